@@ -1,0 +1,85 @@
+"""Pin the oracle (oracle/mn_oracle.py) to outputs of the UNMODIFIED reference.
+
+The reference has no tests or golden vectors of its own, so
+the fixtures under tests/golden/ were produced by running the reference's own
+files on seeded inputs (oracle/make_golden.py).  CPU only.
+"""
+import numpy as np
+import pytest
+
+from oracle import cases as C
+from oracle import mn_oracle as O
+from tests.helpers import assert_table_close, oracle_run
+
+# float64 restatement vs float64 reference: differences are summation-order
+# noise, except that a near-tie in the votes may flip one rank.  The flip
+# quantum at these sizes (n_pos ~ 30, n_neg ~ 130..450) is ~1e-4, so hold the
+# oracle to a tight tolerance and let a genuine flip show up as a failure.
+TIGHT = 1e-9
+
+
+def test_normalize_matches_reference_and_scipy():
+    spec, inp, ref = C.load_case("normalize")
+    got = oracle_run(spec, inp)
+    assert np.array_equal(got["rank2"], ref["rank2"]), "2*rank must be bit-exact"
+    assert np.allclose(got["xnorm"], ref["xnorm"], atol=1e-12, rtol=0, equal_nan=True)
+    import scipy.stats
+    x = inp["X"]
+    assert np.array_equal(O.rank2_rows(x), np.rint(2 * scipy.stats.rankdata(x, "average", axis=1)).astype(np.int64))
+
+
+@pytest.mark.parametrize("name", C.list_cases("us_fast") + C.list_cases("us_default"))
+def test_unsupervised_tables(name):
+    spec, inp, ref = C.load_case(name)
+    got = oracle_run(spec, inp)
+    assert_table_close(got["auroc_values"], got["auroc_rows"], got["auroc_cols"],
+                       ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"], TIGHT, name)
+    if spec.get("p"):
+        assert_table_close(got["pval_values"], got["pval_rows"], got["pval_cols"],
+                           ref["pval_values"], ref["pval_rows"], ref["pval_cols"], 1e-9, name + " pval")
+
+
+def test_train_model():
+    spec, inp, ref = C.load_case("train_model")
+    got = oracle_run(spec, inp)
+    assert_table_close(got["model_values"], got["model_rows"], got["model_cols"],
+                       ref["model_values"], ref["model_rows"], ref["model_cols"], 1e-10, "train_model")
+
+
+@pytest.mark.parametrize("name", C.list_cases("pretrained"))
+def test_pretrained(name):
+    spec, inp, ref = C.load_case(name)
+    train_inp = C.build_inputs(spec["train"])
+    got = oracle_run(spec, inp, train_inp)
+    assert_table_close(got["auroc_values"], got["auroc_rows"], got["auroc_cols"],
+                       ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"], TIGHT, name)
+
+
+@pytest.mark.parametrize("name", C.list_cases("supervised"))
+def test_supervised(name):
+    spec, inp, ref = C.load_case(name)
+    got = oracle_run(spec, inp)
+    assert_table_close(got["auroc_values"], got["auroc_rows"], got["auroc_cols"],
+                       ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"], TIGHT, name)
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_fixture_inputs_rebuild_identically(name):
+    """The seeded generator reproduces the stored inputs (so larger parity
+    cases built from the same generator are the inputs the reference saw)."""
+    spec, inp, _ = C.load_case(name)
+    again = C.build_inputs(spec)
+    assert np.array_equal(again["X"], inp["X"])
+    assert list(again["study"]) == list(inp["study"]) and list(again["ctype"]) == list(inp["ctype"])
+
+
+def test_auroc_cells_match_sklearn():
+    """Independent cross-oracle: every AUROC cell equals sklearn's roc_auc_score."""
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(0)
+    votes = rng.normal(size=(300, 4)).round(1)                # rounding forces ties
+    codes = rng.integers(0, 3, size=300)
+    roc, _, _ = O.compute_aurocs(votes, codes, 3)
+    for c in range(3):
+        for l in range(4):
+            assert abs(roc[c, l] - roc_auc_score(codes == c, votes[:, l])) < 1e-12
