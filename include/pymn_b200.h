@@ -1,0 +1,191 @@
+/*
+ * pymn_b200 -- C ABI of the B200 (sm_100a) MetaNeighbor scoring hot path.
+ *
+ * Drop-in boundary.  The reference (gillislab/pyMN) is
+ * pure Python: its "FFI" for this path is the set of NumPy / bottleneck calls
+ * inside pymn/utils.py, pymn/MetaNeighborUS.py, pymn/MetaNeighbor.py and
+ * pymn/trainModel.py.  Each entry point below replaces one of those call sites
+ * (cited per function, paths relative to the reference's pymn/ directory) and
+ * is what a ctypes stub inside those files would bind.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless it says "host";
+ *  - the caller owns all buffers (inputs, outputs, workspaces); nothing is
+ *    allocated inside and nothing outlives a call except the enqueued work;
+ *  - every call enqueues on the given stream (cudaStream_t passed as void*)
+ *    and returns without synchronising; thread-compatible (one stream per call);
+ *  - return value 0 = success, non-zero = error; mn_last_error() returns the
+ *    message of the last failure on the calling thread;
+ *  - "cells" are rows.  Device-side cell order is the caller's (the Python host
+ *    sorts cells by (test study, label) so that studies and labels are
+ *    contiguous row ranges);
+ *  - fp16 "planes": centred doubled ranks d = 2*rank - (G+1) are integers with
+ *    |d| < G.  d_hi = fp16(d) is exact for G <= 2048; otherwise d = d_hi + d_lo
+ *    exactly with both fp16.  These feed the tcgen05 kind::f16 tensor-core GEMMs
+ *    with FP32 accumulation in TMEM (integer-exact operands instead of a
+ *    3xTF32 split of normalised floats).
+ */
+#ifndef PYMN_B200_H
+#define PYMN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mn_stream_t;   /* cudaStream_t */
+typedef uint16_t mn_half_t;  /* IEEE binary16 bit pattern (__half) */
+
+/* ---- library ------------------------------------------------------------- */
+const char* mn_last_error(void);
+int mn_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t mn_launch_count(void);
+
+/* ---- K1: per-cell rank + normalise --------------------------------------
+ * Replaces normalize_cells (utils.py:122-148: bottleneck.rankdata(axis=1),
+ * centre, L2-normalise) and the ranking half of create_nw_spearman (utils.py:69).
+ *   X          [*, ldx] float32 row-major cells x genes (any finite floats)
+ *   row_index  int32[M] or NULL: output row i is input row row_index[i]
+ *   col_index  int32[G] or NULL: gene g is input column col_index[g]
+ *                (per-gene-set sub-setting, MetaNeighbor.py:85)
+ *   d_hi,d_lo  fp16 [M, ldd] planes (d_lo may be NULL when G <= 2048);
+ *                columns G..ldd-1 are written as zero
+ *   inv_norm   float32[M]: 1/||d||_2, or 0 for a dropped cell
+ *   flags      uint8[M]: bit0 = zero variance (NaN row in the reference,
+ *                utils.py:146-147), bit1 = row sum <= 0 (trainModel.py:36,
+ *                MetaNeighbor.py:121), bit2 = dropped (d = 0, inv_norm = 0)
+ *   xnorm      float32 [M, G] or NULL: the reference's normalised matrix
+ *   rank2      int32 [M, G] or NULL: 2*rank (bit-exact integer encoding)
+ *   drop_mode  0: drop zero-variance cells; 1: drop cells with row sum <= 0
+ *                (zero-variance cells are always zeroed; flags tell them apart)
+ */
+int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index,
+                      int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo, int64_t ldd,
+                      float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
+                      int32_t drop_mode, mn_stream_t stream);
+
+/* ---- K2: cluster centroids ----------------------------------------------
+ * Replaces X_norm @ onehot (MetaNeighborUS.py:284, trainModel.py:43,
+ * MetaNeighbor.py:170 inner product) and n_cells_per_cluster (:288).
+ * Cells are sorted by label: label l owns rows [row_off[l], row_off[l+1]).
+ *   centroids  float32 [L, ldc]  (row l = sum over the label's kept cells of d*inv_norm)
+ *   n_valid    float32 [L]       number of kept cells (inv_norm > 0) per label
+ */
+int mn_centroids(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
+                 const int32_t* row_off, int32_t L, int32_t G, float* centroids, int64_t ldc,
+                 float* n_valid, mn_stream_t stream);
+
+/* out[g_out, :] = sum over rows r with group[r] == g_out of in[r, :]   (rows with group < 0 skipped).
+ * Replaces cluster_centroids @ study_matrix and n_cells_per_cluster @ study_matrix
+ * (MetaNeighborUS.py:349-350).  in/out float32 [R, ld] / [n_groups, ld]; width = columns used. */
+int mn_group_sum(const float* in, int64_t ld, int32_t R, int32_t width, const int32_t* group,
+                 int32_t n_groups, float* out, mn_stream_t stream);
+
+/* Split float32 rows into two fp16 planes with a per-row power-of-two scale:
+ *   in[r, g] ~= (hi[r, g] + lo[r, g]) * inv_scale[r]   (22+ significant bits).
+ * Prepares the centroid operand of mn_votes_fast.  Columns G..ldh-1 zeroed. */
+int mn_split_f16(const float* in, int64_t ld, int32_t R, int32_t G, mn_half_t* hi, mn_half_t* lo,
+                 int64_t ldh, float* inv_scale, mn_stream_t stream);
+
+/* ---- K3: centroid votes (tcgen05 GEMM) ------------------------------------
+ * Replaces votes = X_test.T @ centroids (+ n_cells) and node_degree =
+ * X_test.T @ study_centroids (+ n_cells_per_study) (MetaNeighborUS.py:361-366;
+ * MetaNeighbor.py:170-174).
+ *   out[n, m] = inv_norm[m] * inv_scale[n] * sum_g (a_hi+a_lo)[m, g] * (b_hi+b_lo)[n, g] + addend[n]
+ *   a_*: [M, lda] fp16 cell planes (a_lo may be NULL); b_*: [Nn, ldb] fp16 centroid planes
+ *   out: float32 column-major [Nn, ldo] (ldo >= M): column n is contiguous over cells
+ */
+int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,
+                  const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
+                  const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream);
+
+/* ---- K4/K5: full cell x cell network, never materialised -----------------
+ * Replaces create_nw_spearman + rank (utils.py:35-75: np.corrcoef, one ranking
+ * of all N^2 entries) and the vote products that consume it
+ * (MetaNeighborUS.py:165-169; MetaNeighbor.py:195-217).
+ *
+ * Pass 1: mn_corr_hist   -- rho tiles on tensor cores -> exact histogram of rho
+ *                           over pairs i<j, i in [row0,row1), both cells kept
+ * LUT   : mn_corr_lut    -- histogram -> fixed-point CDF table W = (rank-1)/max
+ * Pass 2: mn_corr_vote   -- rho tiles again -> W via LUT -> integer vote sums
+ *   votes  uint64 [N, L]  sum_j W_fix(rho_ij) [label(j)==l]   (W_fix = W * 2^30; j != i)
+ *   degree uint64 [N]     sum_j W_fix(rho_ij)                 (j != i)
+ * Both accumulate with integer atomics (exact, order-independent, so the
+ * result is bit-identical for any tile schedule or GPU count).  The caller
+ * zeroes hist / votes / degree.  label[j] < 0 excludes cell j as a voter.
+ */
+int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
+                 int64_t N, int64_t row0, int64_t row1, int32_t G, int32_t nbins, uint64_t* hist,
+                 mn_stream_t stream);
+/* n_diag = number of diagonal entries (all cells, they tie at rho = 1 -- utils.py:72) */
+int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut /* [nbins+1] */,
+                mn_stream_t stream);
+int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
+                 int64_t N, int64_t row0, int64_t row1, int32_t G, int32_t nbins, const uint32_t* lut,
+                 const int32_t* label, int32_t L, uint64_t* votes, uint64_t* degree, mn_stream_t stream);
+
+/* votes uint64 [N, L] + degree uint64 [N] -> float32 column-major [L, ldo] vote matrix.
+ * Adds the diagonal (W_ii = 1, utils.py:74) to votes[i, label[i]] and degree[i];
+ * ndn != 0 divides by the node degree (MetaNeighborUS.py:167-169). */
+int mn_votes_finalize(const uint64_t* votes, const uint64_t* degree, const int32_t* label, int64_t N,
+                      int32_t L, int32_t ndn, float* out, int64_t ldo, mn_stream_t stream);
+
+/* Leave-one-study-out combination for the supervised paths (MetaNeighbor.py:198-217
+ * and :134-147,170-175).  Input: per-cell sums over joint (study, type) labels,
+ * joint id = study * K + type, either uint64 fixed-point [N, S*K] (full network,
+ * is_fixed = 1; `degree` uint64 [N] is the node degree incl. the diagonal = W_ii)
+ * or float32 column-major [S*K, ldi] (centroid votes, is_fixed = 0; n_joint
+ * float32 [S*K] = kept cells per joint label).  Output float32 column-major [K, ldo]:
+ *   out[k, i] = sum_{s' != study(i)} in[i, (s', k)]  (+ n_k of other studies)  / degree
+ */
+int mn_loso_finalize(const void* in, int64_t ldi, int32_t is_fixed, const uint64_t* degree,
+                     const float* n_joint, const int32_t* cell_study, int64_t N, int32_t S, int32_t K,
+                     int32_t ndn, float* out, int64_t ldo, mn_stream_t stream);
+
+/* ---- K6: rank-sum AUROC --------------------------------------------------
+ * Replaces compute_aurocs (utils.py:151-178), compute_aurocs_default
+ * (MetaNeighborUS.py:194-213) and the rank-sum block of score_default
+ * (MetaNeighbor.py:232-238).
+ *   votes     float32 column-major [ncols, ldv]; column l = votes of all cells for train label l
+ *   denom     float32 column-major [n_denom, ldv] or NULL; col_denom int32[ncols] (or NULL):
+ *               key = votes[l, i] / denom[col_denom[l], i]   (node degree per train study,
+ *               MetaNeighborUS.py:365-371)
+ *   seg_off   int32[n_seg+1]: test study t owns cells [seg_off[t], seg_off[t+1])
+ *   cell_label int32[M]: test-label id of each cell (0..n_labels-1), or < 0 = cell excluded
+ *   auroc     float64 [n_labels, ncols]: rows = test labels, cols = train labels
+ *               (a label's row is filled from the segment its cells are in)
+ *   n_pos     int32 [n_labels] or NULL: kept cells per test label
+ *   workspace from mn_auroc_workspace_bytes(ncols, M)
+ * Ranks are exact average-tie ranks of the float32 keys (integer 2*rank sums).
+ */
+int64_t mn_auroc_workspace_bytes(int32_t ncols, int64_t M);
+int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom, const int32_t* col_denom,
+             const int32_t* seg_off, int32_t n_seg, const int32_t* cell_label, int32_t n_labels, int64_t M,
+             double* auroc, int32_t* n_pos, void* workspace, int64_t workspace_bytes, mn_stream_t stream);
+
+/* ---- K7: one-vs-best ------------------------------------------------------
+ * Replaces compute_1v1_aurocs + find_top_candidates (utils.py:194-248).
+ * Cells must be sorted by label inside each segment: label c owns rows
+ * [lab_row_off[c], lab_row_off[c+1]) (excluded cells have inv. keys skipped via
+ * cell_label < 0).  seg_lab_off int32[n_seg+1]: segment t owns labels
+ * [seg_lab_off[t], seg_lab_off[t+1]).  out float64 [n_labels, ncols] must be
+ * pre-filled with NaN by the caller; two cells per (segment, column) are written.
+ */
+int mn_one_vs_best(const float* votes, int64_t ldv, int32_t ncols, const float* denom,
+                   const int32_t* col_denom, const int32_t* seg_lab_off, int32_t n_seg,
+                   const int32_t* lab_row_off, const int32_t* cell_label, int32_t n_labels,
+                   const double* auroc, double* out, mn_stream_t stream);
+
+/* ---- debug / test-only -----------------------------------------------------
+ * Plain CUDA-core GEMM with the same contract as mn_votes_fast; used by the
+ * tests to cross-check the tcgen05 kernel on device.  Not on any product path. */
+int mn_debug_votes_simt(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,
+                        const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
+                        const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMN_B200_H */

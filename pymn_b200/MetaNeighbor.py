@@ -1,0 +1,125 @@
+"""Drop-in supervised ``MetaNeighbor`` (reference pymn/MetaNeighbor.py:11-103).
+
+Gene sets are independent (MetaNeighbor.py:84-93): when ``torch.distributed``
+is initialised with more than one rank, the gene-set columns are dealt
+round-robin to the ranks (one process per GPU, expression matrix replicated)
+and the K x n_sets result is assembled with one all-gather.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from . import engine
+from .utils import joint_layout, to_dense_f32
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def shard_columns(n_sets: int, rank: int, world: int) -> np.ndarray:
+    """Static round-robin assignment of gene-set columns to ranks."""
+    return np.arange(rank, n_sets, world)
+
+
+def gather_columns(local: np.ndarray, n_sets: int, rank: int, world: int) -> np.ndarray:
+    """All-gather the per-rank K x n_local blocks back into K x n_sets (column j
+    lives on rank j % world).  Uses the default process group (NCCL on GPUs,
+    gloo in the CPU tests)."""
+    if world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+    K = local.shape[0]
+    n_max = (n_sets + world - 1) // world
+    buf = np.full((K, n_max), np.nan)
+    buf[:, :local.shape[1]] = local
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.full((K, n_sets), np.nan)
+    for r in range(world):
+        cols = shard_columns(n_sets, r, world)
+        out[:, cols] = parts[r].cpu().numpy()[:, :len(cols)]
+    return out
+
+
+def _reduce_over_studies(auc: np.ndarray, S: int, K: int) -> np.ndarray:
+    """auc [S*K, K] (rows = joint test labels) -> per-type mean over studies of the
+    diagonal entries AUROC[(s, k), k]  (MetaNeighbor.py:147-148, :241-245)."""
+    diag = auc.reshape(S, K, K)[:, np.arange(K), np.arange(K)]       # [S, K]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return np.nanmean(diag, axis=0)
+
+
+def MetaNeighbor(
+    adata,
+    study_col,
+    ct_col,
+    genesets,
+    node_degree_normalization=True,
+    save_uns=True,
+    fast_version=False,
+    fast_hi_mem=False,
+    mn_key="MetaNeighbor",
+):
+    """Supervised MetaNeighbor; arguments as in reference pymn/MetaNeighbor.py:22-53.
+    ``fast_hi_mem`` is accepted for compatibility (the expression matrix always
+    lives densely in HBM here)."""
+    assert study_col in adata.obs_keys(), "Study Col not in adata"
+    assert ct_col in adata.obs_keys(), "Cluster Col not in adata"
+    assert (
+        np.unique(adata.obs[study_col]).shape[0] > 1
+    ), f"Found only 1 unique study_id in {study_col}"
+
+    shared_genes = np.intersect1d(adata.var_names.values, genesets.index.values)
+    assert (
+        shared_genes.shape[0] > 1
+    ), "No matching genes between genesets and sample matrix"
+
+    genesets = genesets.loc[shared_genes]
+    genesets = genesets.loc[:, genesets.sum() > 0]
+
+    assert genesets.shape[1] > 0, "All Genesets are empty"
+    genesets = genesets.astype(bool)
+
+    study_vec = adata.obs[study_col].values
+    ct_vec = adata.obs[ct_col].values
+    expression = to_dense_f32(adata[:, shared_genes].X)
+    lay, ct_names = joint_layout(study_vec, ct_vec)
+    S, K = len(lay.studies), len(ct_names)
+
+    rank, world = _dist_info()
+    gs_values = genesets.values
+    n_sets = gs_values.shape[1]
+    mine = shard_columns(n_sets, rank, world)
+    Xd, perm_dev = engine.supervised_prepare(expression, lay)
+    local = np.full((K, len(mine)), np.nan)
+    for jj, j in enumerate(mine):
+        cols = np.flatnonzero(gs_values[:, j]).astype(np.int32)
+        auc = engine.supervised_geneset(Xd, perm_dev, cols, lay, K, bool(node_degree_normalization),
+                                        bool(fast_version))
+        local[:, jj] = _reduce_over_studies(auc.cpu().numpy(), S, K)
+    table = gather_columns(local, n_sets, rank, world)
+    results = pd.DataFrame(table, index=ct_names, columns=genesets.columns)
+    if save_uns:
+        adata.uns[mn_key] = results
+        adata.uns[f"{mn_key}_params"] = {
+            "fast": fast_version,
+            "node_degree_normalization": node_degree_normalization,
+            "study_col": study_col,
+            "ct_col": ct_col,
+        }
+    else:
+        return results

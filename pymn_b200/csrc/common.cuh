@@ -1,0 +1,87 @@
+// Shared helpers for the pymn_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pymn_b200.h"
+
+namespace mn {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MN_CHECK_ARG(cond, ...)              \
+    do {                                     \
+        if (!(cond)) {                       \
+            mn::set_error(__VA_ARGS__);      \
+            return 1;                        \
+        }                                    \
+    } while (0)
+
+#define MN_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            mn::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define MN_LAUNCH_CHECK()                                                                 \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            mn::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return 3;                                                                     \
+        }                                                                                 \
+        mn::count_launch();                                                               \
+    } while (0)
+
+// order-preserving map float -> uint32 (ascending floats -> ascending keys)
+__device__ __forceinline__ uint32_t float_key(float v) {
+    uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; scratch must hold >= 32 elements of T; all threads get the result.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T t = (threadIdx.x < nw) ? scratch[threadIdx.x] : T(0);
+    if (warp == 0) {
+        t = warp_sum(t);
+        if (lane == 0) scratch[0] = t;
+    }
+    __syncthreads();
+    t = scratch[0];
+    return t;
+}
+
+static inline int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace mn

@@ -1,0 +1,705 @@
+// K3 / K4 / K5: tcgen05 tensor-core contraction with fused epilogues (sm_100a).
+//
+//   D[m, n] = sum_g A[m, g] * B[n, g]        A, B: K-major fp16 planes, D: FP32 in TMEM
+//
+// Operands are the integer-valued centred doubled ranks d = 2*rank - (G+1)
+// written by K1 as fp16 planes (exact: one plane for G <= 2048, hi+lo beyond),
+// so the tensor cores multiply EXACT integers and only the FP32 accumulation
+// rounds; the 1/||d|| scaling happens in the epilogue.  (The reference computes
+// the same quantity as np.corrcoef of the ranks, utils.py:71, or as dot
+// products of normalised cells, MetaNeighborUS.py:361.)  Multi-plane products
+// (hi*hi + hi*lo + lo*hi) are extra accumulation passes into the same TMEM
+// accumulator -- the fp16 analogue of a 3xTF32 split, but with exact limbs.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) -> smem ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1,
+//               kind::f16, M=128, N=BN, K=16), tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) from one of
+//               two TMEM accumulator stages while the next tile's MMAs run
+// Epilogues:
+//   EPI_STORE  votes_fast: scale + addend, store column-major FP32   (MetaNeighborUS.py:361-366)
+//   EPI_HIST   pass 1 of the global rank: rho -> shared-memory histogram (utils.py:44-45)
+//   EPI_VOTE   pass 2: rho -> W via CDF LUT -> integer per-label vote sums + node degree
+//              (utils.py:46-51 + MetaNeighborUS.py:165-169); the N x N network never exists.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mn {
+
+constexpr int BM = 128;            // rows per tile = TMEM lanes
+constexpr int BK = 64;             // fp16 elements per k-block = 128 bytes = one swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_STAGES = 6;
+constexpr int MAX_TERMS = 4;
+
+enum { EPI_STORE = 0, EPI_HIST = 1, EPI_VOTE = 2 };
+
+struct GemmParams {
+    int64_t M;        // rows of A
+    int64_t N;        // rows of B
+    int k_blocks;     // ceil(G / 64)
+    int n_terms;      // plane products accumulated into one tile
+    int a_sel[MAX_TERMS];   // 0 = hi plane, 1 = lo plane
+    int b_sel[MAX_TERMS];
+    int tri;          // 1: only tiles that contain some column index > row index
+    int mt0, mt1;     // row-tile range handled by this launch
+    int n_tiles;      // number of column tiles
+    int stages;
+    // epilogue
+    const float* inv_a;      // [M] row scale (1/||d||), 0 = dropped cell
+    const float* inv_b;      // [N] column scale
+    const float* addend;     // [N] or null            (EPI_STORE)
+    float* out;              // column-major [N, ldo]  (EPI_STORE)
+    int64_t ldo;
+    int nbins;               // power of two           (EPI_HIST / EPI_VOTE)
+    unsigned long long* hist;      // [nbins]          (EPI_HIST)
+    const uint32_t* lut;     // [nbins + 1]            (EPI_VOTE)
+    const int32_t* label;    // [N]                    (EPI_VOTE)
+    int L;
+    unsigned long long* votes;     // [M, L]
+    unsigned long long* degree;    // [M]
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Spin until the barrier phase with the given parity completes.  A wait that lasts
+// longer than ~10 s of SM clocks can only be a protocol bug: trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(addr, parity)) {
+        if (clock64() - t0 > 20000000000ll) {
+            printf("pymn_b200 gemm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: 8-row groups of 1024 bytes (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+// kind::f16, A=B=F16, D=F32, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// position of rho on the bin axis; pass 1 and pass 2 must agree bit for bit
+__device__ __forceinline__ float rho_binpos(float acc, float inv_i_half, float inv_j, float half_bins) {
+    return fmaf(acc * inv_i_half, inv_j, half_bins);      // (rho + 1) * nbins / 2
+}
+
+// ------------------------------------------------------------------ tile schedule
+struct TileIter {
+    int mt, nt_rel, mt1, n_tiles, tri, bn;
+    __device__ __forceinline__ int first_nt(int m) const { return tri ? (m * BM) / bn : 0; }
+    __device__ __forceinline__ int len(int m) const { return n_tiles - first_nt(m); }
+    __device__ __forceinline__ void init(const GemmParams& p, int bn_, int start) {
+        mt = p.mt0; mt1 = p.mt1; n_tiles = p.n_tiles; tri = p.tri; bn = bn_;
+        nt_rel = 0;
+        advance(start);
+    }
+    __device__ __forceinline__ void advance(int step) {
+        long long rem = (long long)nt_rel + step;
+        while (mt < mt1 && rem >= len(mt)) {
+            rem -= len(mt);
+            ++mt;
+        }
+        nt_rel = (int)rem;
+    }
+    __device__ __forceinline__ bool valid() const { return mt < mt1; }
+    __device__ __forceinline__ int nt() const { return first_nt(mt) + nt_rel; }
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+            const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr uint32_t A_BYTES = BM * BK * 2;
+    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+    // carve-up: [stages * STAGE_BYTES] operand ring (1024-aligned) | epilogue table | barriers etc.
+    unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
+    unsigned char* tail = ring + (size_t)p.stages * STAGE_BYTES;
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(tail);                 // hist [nbins] or lut [nbins+1]
+    const int table_words = (EPI == EPI_STORE) ? 0 : (p.nbins + 1 + 3) & ~3;
+    float* s_invb = reinterpret_cast<float*>(s_table + table_words);       // [BN]
+    int32_t* s_lab = reinterpret_cast<int32_t*>(s_invb + BN);              // [BN]
+    float* s_add = reinterpret_cast<float*>(s_lab + BN);                   // [BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_add + BN);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + MAX_STAGES;
+    uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
+    uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_iters = p.n_terms * p.k_blocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_b_hi);
+        if (p.n_terms > 1) {
+            tma_prefetch_desc(&tm_a_lo);
+            tma_prefetch_desc(&tm_b_lo);
+        }
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (EPI != EPI_STORE) {
+        // hist starts at zero; lut is copied in
+        for (int i = threadIdx.x; i < p.nbins + 1; i += GEMM_THREADS)
+            s_table[i] = (EPI == EPI_VOTE) ? p.lut[i] : 0u;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            TileIter it;
+            it.init(p, BN, blockIdx.x);
+            int s = 0;
+            uint32_t ph = 0;
+            for (; it.valid(); it.advance(gridDim.x)) {
+                const int m0 = it.mt * BM, n0 = it.nt() * BN;
+                for (int term = 0; term < p.n_terms; ++term) {
+                    const CUtensorMap* ma = p.a_sel[term] ? &tm_a_lo : &tm_a_hi;
+                    const CUtensorMap* mb = p.b_sel[term] ? &tm_b_lo : &tm_b_hi;
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        unsigned char* sa = ring + (size_t)s * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                        tma_load_2d(sa, ma, &full_bar[s], kb * BK, m0);
+                        tma_load_2d(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                        if (++s == p.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BM, BN);
+            TileIter it;
+            it.init(p, BN, blockIdx.x);
+            int s = 0, a = 0;
+            uint32_t ph = 0, aph = 0;
+            for (; it.valid(); it.advance(gridDim.x)) {
+                mbar_wait(&tempty_bar[a], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                for (int i = 0; i < n_iters; ++i) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(ring + (size_t)s * STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance the start address by k * 16 elements * 2 B = 32 B = 2 (16-byte units)
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                   (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[s]);      // frees the smem slot once these MMAs retire
+                    if (++s == p.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+                tc_commit(&tfull_bar[a]);          // accumulator complete -> epilogue
+                if (++a == 2) {
+                    a = 0;
+                    aph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
+        const int row_in_tile = q * 32 + lane;
+        TileIter it;
+        it.init(p, BN, blockIdx.x);
+        int a = 0;
+        uint32_t aph = 0;
+        const float half_bins = 0.5f * (float)p.nbins;
+        for (; it.valid(); it.advance(gridDim.x)) {
+            const int64_t m0 = (int64_t)it.mt * BM, n0 = (int64_t)it.nt() * BN;
+            const int64_t m = m0 + row_in_tile;
+            // stage per-column metadata of this tile
+            epi_bar_sync();                           // previous tile's readers are done
+            for (int c = et; c < BN; c += 128) {
+                const int64_t n = n0 + c;
+                const bool ok = n < p.N;
+                s_invb[c] = ok ? p.inv_b[n] : 0.f;
+                if (EPI == EPI_STORE) s_add[c] = (ok && p.addend) ? p.addend[n] : 0.f;
+                if (EPI == EPI_VOTE) s_lab[c] = ok ? p.label[n] : -1;
+            }
+            epi_bar_sync();
+            const bool row_ok = m < p.M;
+            const float inv_i = row_ok ? p.inv_a[m] : 0.f;
+
+            mbar_wait(&tfull_bar[a], aph);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+
+            if (EPI == EPI_STORE) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(t_base + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int64_t n = n0 + c0 + c;
+                            if (n < p.N)
+                                p.out[n * p.ldo + m] = fmaf(__uint_as_float(r[c]) * inv_i, s_invb[c0 + c], s_add[c0 + c]);
+                        }
+                    }
+                }
+            } else if (EPI == EPI_HIST) {
+                const float inv_i_half = inv_i * half_bins;
+                const bool diag_tile = (n0 <= m0 + BM - 1);       // some column index <= some row index
+                const int maxbin = p.nbins - 1;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(t_base + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    if (inv_i > 0.f) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float inv_j = s_invb[c0 + c];
+                            const bool use = (inv_j > 0.f) && (!diag_tile || (n0 + c0 + c > m));
+                            if (use) {
+                                const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                                int b = __float2int_rd(pos);
+                                b = min(max(b, 0), maxbin);
+                                atomicAdd(&s_table[b], 1u);
+                            }
+                        }
+                    }
+                }
+            } else {   // EPI_VOTE
+                const float inv_i_half = inv_i * half_bins;
+                const int maxbin = p.nbins - 1;
+                unsigned long long deg_acc = 0ull, run_acc = 0ull;
+                int cur_lab = -1;
+                unsigned long long* vrow = p.votes + (row_ok ? m : 0) * (int64_t)p.L;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(t_base + (uint32_t)c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int lab = s_lab[c0 + c];           // warp-uniform
+                        if (lab != cur_lab) {
+                            if (run_acc && cur_lab >= 0) atomicAdd(vrow + cur_lab, run_acc);
+                            run_acc = 0ull;
+                            cur_lab = lab;
+                        }
+                        const float inv_j = s_invb[c0 + c];
+                        const bool use = (inv_i > 0.f) && (inv_j > 0.f) && (n0 + c0 + c != m);
+                        if (use) {
+                            const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                            int b = __float2int_rd(pos);
+                            b = min(max(b, 0), maxbin);
+                            const float frac = fminf(fmaxf(pos - (float)b, 0.f), 1.f);
+                            const uint32_t lo = s_table[b], hi = s_table[b + 1];
+                            const uint32_t w = lo + __float2uint_rd(frac * (float)(hi - lo));
+                            deg_acc += w;
+                            if (lab >= 0) run_acc += w;
+                        }
+                    }
+                }
+                if (run_acc && cur_lab >= 0) atomicAdd(vrow + cur_lab, run_acc);
+                if (deg_acc && row_ok) atomicAdd(p.degree + m, deg_acc);
+            }
+
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            if (++a == 2) {
+                a = 0;
+                aph ^= 1u;
+            }
+        }
+        if (EPI == EPI_HIST) {
+            epi_bar_sync();
+            for (int b = et; b < p.nbins; b += 128) {
+                const uint32_t v = s_table[b];
+                if (v) atomicAdd(p.hist + b, (unsigned long long)v);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ CDF LUT
+// hist: counts of rho over pairs i<j.  Ranking covers both triangles plus the
+// n_diag diagonal entries, which tie at the top (utils.py:72).  For a value at
+// fraction t of bin b:  rank - 1 ~= 2*(cum[b] + t*cnt[b]);  W = (rank-1)/top with
+// top = F - (n_diag-1)/2 - 1, F = 2*total + n_diag (utils.py:47-49).  lut[b] = W at the
+// lower edge of bin b in 2^30 fixed point, lut[nbins] = W at the upper edge.
+__global__ void corr_lut_kernel(const unsigned long long* __restrict__ hist, int nbins, long long n_diag,
+                                uint32_t* __restrict__ lut) {
+    __shared__ unsigned long long s_part[1024];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int per = (nbins + T - 1) / T;
+    const int b0 = tid * per, b1 = min(nbins, b0 + per);
+    unsigned long long local = 0;
+    for (int b = b0; b < b1; ++b) local += hist[b];
+    s_part[tid] = local;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < T; ++i) {
+            const unsigned long long v = s_part[i];
+            s_part[i] = run;
+            run += v;
+        }
+        s_part[T] = run;      // T < 1024 is guaranteed by the launcher
+    }
+    __syncthreads();
+    const double total = (double)s_part[T];
+    const double F = 2.0 * total + (double)n_diag;
+    double top = F - ((double)n_diag - 1.0) * 0.5 - 1.0;
+    if (!(top > 0.0)) top = 1.0;
+    const double scale = 1073741824.0 / top;
+    unsigned long long run = s_part[tid];
+    for (int b = b0; b < b1; ++b) {
+        lut[b] = (uint32_t)fmin(1073741824.0, rint(2.0 * (double)run * scale));
+        run += hist[b];
+    }
+    if (tid == 0) lut[nbins] = (uint32_t)fmin(1073741824.0, rint(2.0 * total * scale));
+}
+
+// ------------------------------------------------------------------ debug reference (CUDA cores)
+__global__ void debug_votes_simt_kernel(const __half* a_hi, const __half* a_lo, int64_t lda, const float* inv_norm,
+                                        int64_t M, const __half* b_hi, const __half* b_lo, int64_t ldb,
+                                        const float* inv_scale, const float* addend, int Nn, int G, float* out,
+                                        int64_t ldo) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (m >= M || n >= Nn) return;
+    double acc = 0.0;
+    for (int g = 0; g < G; ++g) {
+        double a = (double)__half2float(a_hi[m * lda + g]);
+        if (a_lo) a += (double)__half2float(a_lo[m * lda + g]);
+        double b = (double)__half2float(b_hi[(int64_t)n * ldb + g]);
+        if (b_lo) b += (double)__half2float(b_lo[(int64_t)n * ldb + g]);
+        acc += a * b;
+    }
+    out[(int64_t)n * ldo + m] = (float)(acc * (double)inv_norm[m] * (double)inv_scale[n] + (addend ? (double)addend[n] : 0.0));
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// rows x cols fp16, row pitch ld elements; box = 64 columns x box_rows rows, 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return 4;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%lld cols=%lld ld=%lld box_rows=%d base=%p)", (int)r,
+                  (long long)rows, (long long)cols, (long long)ld, box_rows, base);
+        return 5;
+    }
+    return 0;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, const __half* b_hi,
+                       const __half* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const int64_t cols_a = lda, cols_b = ldb;     // padding columns are zero; beyond ld the TMA zero-fills
+    int rc;
+    if ((rc = make_map(&ta_hi, a_hi, M, cols_a, lda, BM))) return rc;
+    if ((rc = make_map(&ta_lo, a_lo ? a_lo : a_hi, M, cols_a, lda, BM))) return rc;
+    if ((rc = make_map(&tb_hi, b_hi, N, cols_b, ldb, BN))) return rc;
+    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, N, cols_b, ldb, BN))) return rc;
+    p.M = M;
+    p.N = N;
+    p.k_blocks = (G + BK - 1) / BK;
+    p.n_tiles = (int)((N + BN - 1) / BN);
+    const size_t stage_bytes = (size_t)(BM + BN) * BK * 2;
+    const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 1 + 3) & ~3) * 4;
+    const size_t fixed = table + (size_t)BN * 12 + (2 * MAX_STAGES + 4) * 8 + 16;
+    const size_t budget = 232448 - 1024;          // 227 KB minus alignment slack
+    int stages = (int)((budget - fixed) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) {
+        set_error("gemm: not enough shared memory for 2 pipeline stages (nbins=%d)", p.nbins);
+        return 6;
+    }
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
+    auto kern = gemm_kernel<BN, EPI>;
+    MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // number of tiles
+    long long tiles = 0;
+    for (int mt = p.mt0; mt < p.mt1; ++mt) tiles += p.n_tiles - (p.tri ? (mt * BM) / BN : 0);
+    if (tiles <= 0) return 0;
+    int grid = sm_count();
+    if (tiles < grid) grid = (int)tiles;
+    kern<<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+static int check_planes(const char* who, const void* hi, int64_t ld, int G) {
+    MN_CHECK_ARG(hi != nullptr, "%s: null plane", who);
+    MN_CHECK_ARG((reinterpret_cast<uintptr_t>(hi) & 15) == 0, "%s: plane must be 16-byte aligned", who);
+    MN_CHECK_ARG(ld >= G && (ld % 8) == 0, "%s: ld=%lld must be >= G=%d and a multiple of 8", who, (long long)ld, G);
+    return 0;
+}
+
+}  // namespace mn
+
+extern "C" {
+
+int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,
+                  const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
+                  const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream) {
+    using namespace mn;
+    if (check_planes("mn_votes_fast(a)", a_hi, lda, G) || check_planes("mn_votes_fast(b)", b_hi, ldb, G)) return 1;
+    MN_CHECK_ARG(inv_norm && inv_scale && out && M >= 1 && Nn >= 1 && ldo >= M, "mn_votes_fast: bad arguments");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int t = 0;
+    p.a_sel[t] = 0; p.b_sel[t] = 0; ++t;
+    if (b_lo) { p.a_sel[t] = 0; p.b_sel[t] = 1; ++t; }
+    if (a_lo) { p.a_sel[t] = 1; p.b_sel[t] = 0; ++t; }
+    p.n_terms = t;
+    p.tri = 0;
+    p.mt0 = 0;
+    p.mt1 = (int)((M + BM - 1) / BM);
+    p.inv_a = inv_norm;
+    p.inv_b = inv_scale;
+    p.addend = addend;
+    p.out = out;
+    p.ldo = ldo;
+    const __half* ah = reinterpret_cast<const __half*>(a_hi);
+    const __half* al = reinterpret_cast<const __half*>(a_lo);
+    const __half* bh = reinterpret_cast<const __half*>(b_hi);
+    const __half* bl = reinterpret_cast<const __half*>(b_lo);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Nn <= 64) return launch_gemm<64, EPI_STORE>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
+    if (Nn <= 128) return launch_gemm<128, EPI_STORE>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
+    return launch_gemm<256, EPI_STORE>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
+}
+
+static int corr_terms(mn::GemmParams& p, bool has_lo) {
+    int t = 0;
+    p.a_sel[t] = 0; p.b_sel[t] = 0; ++t;
+    if (has_lo) {
+        p.a_sel[t] = 0; p.b_sel[t] = 1; ++t;
+        p.a_sel[t] = 1; p.b_sel[t] = 0; ++t;
+        p.a_sel[t] = 1; p.b_sel[t] = 1; ++t;      // lo*lo too: the integer product stays exact
+    }
+    return t;
+}
+
+int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t N,
+                 int64_t row0, int64_t row1, int32_t G, int32_t nbins, uint64_t* hist, mn_stream_t stream) {
+    using namespace mn;
+    if (check_planes("mn_corr_hist", d_hi, ldd, G)) return 1;
+    MN_CHECK_ARG(inv_norm && hist && N >= 1 && row0 >= 0 && row1 <= N && row0 < row1, "mn_corr_hist: bad arguments");
+    MN_CHECK_ARG(nbins >= 256 && nbins <= 32768 && (nbins & (nbins - 1)) == 0, "mn_corr_hist: nbins must be a power of two in [256, 32768]");
+    MN_CHECK_ARG((row0 % BM) == 0, "mn_corr_hist: row0 must be a multiple of %d", BM);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_terms = corr_terms(p, d_lo != nullptr);
+    p.tri = 1;
+    p.mt0 = (int)(row0 / BM);
+    p.mt1 = (int)((row1 + BM - 1) / BM);
+    p.inv_a = inv_norm;
+    p.inv_b = inv_norm;
+    p.nbins = nbins;
+    p.hist = reinterpret_cast<unsigned long long*>(hist);
+    const __half* h = reinterpret_cast<const __half*>(d_hi);
+    const __half* l = reinterpret_cast<const __half*>(d_lo);
+    // rows beyond row1 inside the last tile belong to the next shard: mask them via M
+    return launch_gemm<128, EPI_HIST>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+}
+
+int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut, mn_stream_t stream) {
+    MN_CHECK_ARG(hist && lut && nbins >= 256 && nbins <= 32768, "mn_corr_lut: bad arguments");
+    mn::corr_lut_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(hist), nbins,
+                                                            (long long)n_diag, lut);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t N,
+                 int64_t row0, int64_t row1, int32_t G, int32_t nbins, const uint32_t* lut, const int32_t* label,
+                 int32_t L, uint64_t* votes, uint64_t* degree, mn_stream_t stream) {
+    using namespace mn;
+    if (check_planes("mn_corr_vote", d_hi, ldd, G)) return 1;
+    MN_CHECK_ARG(inv_norm && lut && label && votes && degree && N >= 1 && L >= 1 && row0 >= 0 && row1 <= N && row0 < row1,
+                 "mn_corr_vote: bad arguments");
+    MN_CHECK_ARG(nbins >= 256 && nbins <= 32768 && (nbins & (nbins - 1)) == 0, "mn_corr_vote: nbins must be a power of two in [256, 32768]");
+    MN_CHECK_ARG((row0 % BM) == 0, "mn_corr_vote: row0 must be a multiple of %d", BM);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_terms = corr_terms(p, d_lo != nullptr);
+    p.tri = 0;
+    p.mt0 = (int)(row0 / BM);
+    p.mt1 = (int)((row1 + BM - 1) / BM);
+    p.inv_a = inv_norm;
+    p.inv_b = inv_norm;
+    p.nbins = nbins;
+    p.lut = lut;
+    p.label = label;
+    p.L = L;
+    p.votes = reinterpret_cast<unsigned long long*>(votes);
+    p.degree = reinterpret_cast<unsigned long long*>(degree);
+    const __half* h = reinterpret_cast<const __half*>(d_hi);
+    const __half* l = reinterpret_cast<const __half*>(d_lo);
+    return launch_gemm<128, EPI_VOTE>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+}
+
+int mn_debug_votes_simt(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,
+                        const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
+                        const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream) {
+    MN_CHECK_ARG(a_hi && b_hi && inv_norm && inv_scale && out, "mn_debug_votes_simt: null pointer");
+    dim3 grid((unsigned)((M + 127) / 128), (unsigned)Nn);
+    mn::debug_votes_simt_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(a_hi), reinterpret_cast<const __half*>(a_lo), lda, inv_norm, M,
+        reinterpret_cast<const __half*>(b_hi), reinterpret_cast<const __half*>(b_lo), ldb, inv_scale, addend, Nn, G,
+        out, ldo);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+}

@@ -1,0 +1,275 @@
+"""Device pipelines of the MetaNeighbor hot path.
+
+Thin Python over the C ABI (``_lib.call``): allocates torch CUDA buffers,
+enqueues the kernels of ``libpymn_b200.so`` on the current stream and returns
+small result tables to the host.  No arithmetic of the hot path happens here
+(torch is plumbing: memory, streams, H2D/D2H); the few torch ops used are
+index bookkeeping on O(N) int vectors and concatenation of O(L) vectors.
+
+Pipelines (reference call stacks in SURVEY.md section 3):
+  us_fast          metaNeighborUS_fast + predict_and_score   MetaNeighborUS.py:228-387
+  us_pretrained    MetaNeighborUS_from_trained               MetaNeighborUS.py:391-430
+  us_default       metaNeighborUS_default                    MetaNeighborUS.py:145-224, utils.py:35-75
+  train_model      trainModel                                trainModel.py:29-48
+  supervised_*     score_default / score_low_mem             MetaNeighbor.py:106-245
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .utils import LabelLayout
+
+DEFAULT_NBINS = 32768      # CDF resolution of the global rank (bins over rho in [-1, 1])
+
+
+def _dev():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(x, dtype=None):
+    """numpy / torch -> contiguous CUDA tensor (pinned staging for numpy)."""
+    dev = _dev()
+    if isinstance(x, torch.Tensor):
+        t = x.to(dev, non_blocking=True)
+    else:
+        a = np.ascontiguousarray(x)
+        t = torch.from_numpy(a)
+        if a.nbytes >= (1 << 20):
+            t = t.pin_memory()
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _i32(a):
+    return to_device(np.asarray(a, dtype=np.int32))
+
+
+@dataclass
+class RankedCells:
+    d_hi: torch.Tensor
+    d_lo: torch.Tensor | None
+    ldd: int
+    inv_norm: torch.Tensor
+    flags: torch.Tensor
+    M: int
+    G: int
+    xnorm: torch.Tensor | None = None
+    rank2: torch.Tensor | None = None
+
+
+def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
+                   want_xnorm=False, want_rank2=False) -> RankedCells:
+    """K1.  X: float32 CUDA [N, Gx] row-major."""
+    assert X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
+    dev = X.device
+    M = int(row_index.numel()) if row_index is not None else int(X.shape[0])
+    G = int(col_index.numel()) if col_index is not None else int(X.shape[1])
+    ldd = (G + 63) // 64 * 64
+    d_hi = torch.empty((M, ldd), dtype=torch.float16, device=dev)
+    d_lo = torch.empty((M, ldd), dtype=torch.float16, device=dev) if G > 2048 else None
+    inv_norm = torch.empty((M,), dtype=torch.float32, device=dev)
+    flags = torch.empty((M,), dtype=torch.uint8, device=dev)
+    xnorm = torch.empty((M, G), dtype=torch.float32, device=dev) if want_xnorm else None
+    rank2 = torch.empty((M, G), dtype=torch.int32, device=dev) if want_rank2 else None
+    if M > 0:
+        _lib.call("mn_rank_normalize", X, int(X.stride(0)), row_index, col_index, M, G, d_hi, d_lo, ldd,
+                  inv_norm, flags, xnorm, rank2, int(drop_mode))
+    return RankedCells(d_hi, d_lo, ldd, inv_norm, flags, M, G, xnorm, rank2)
+
+
+def centroids(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: int = 0):
+    """K2.  Returns (C float32 [L + extra_rows, ldd] (extra rows zero), n_valid float32 [L + extra_rows])."""
+    C = torch.zeros((L + extra_rows, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)
+    n_valid = torch.zeros((L + extra_rows,), dtype=torch.float32, device=rc.d_hi.device)
+    _lib.call("mn_centroids", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, row_off, L, rc.G, C, rc.ldd, n_valid)
+    return C, n_valid
+
+
+def group_sum_into(C, n_valid, L, group: torch.Tensor, n_groups: int, width: int):
+    """Study centroids / study sizes appended as rows L.. of C / n_valid."""
+    ld = int(C.stride(0))
+    _lib.call("mn_group_sum", C, ld, L, width, group, n_groups, C[L:])
+    _lib.call("mn_group_sum", n_valid, 1, L, 1, group, n_groups, n_valid[L:])
+
+
+def split_f16(C: torch.Tensor, G: int):
+    R, ld = int(C.shape[0]), int(C.stride(0))
+    hi = torch.empty((R, ld), dtype=torch.float16, device=C.device)
+    lo = torch.empty((R, ld), dtype=torch.float16, device=C.device)
+    inv_scale = torch.empty((R,), dtype=torch.float32, device=C.device)
+    _lib.call("mn_split_f16", C, ld, R, G, hi, lo, ld, inv_scale)
+    return hi, lo, inv_scale
+
+
+def votes_fast(rc: RankedCells, b_hi, b_lo, inv_scale, addend, Nn: int, debug_simt=False):
+    """K3.  Returns float32 [Nn, M] (column-major votes: one row per train column)."""
+    out = torch.empty((Nn, rc.M), dtype=torch.float32, device=rc.d_hi.device)
+    name = "mn_debug_votes_simt" if debug_simt else "mn_votes_fast"
+    _lib.call(name, rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, rc.M, b_hi, b_lo, int(b_hi.stride(0)), inv_scale,
+              addend, Nn, rc.G, out, rc.M)
+    return out
+
+
+def auroc(votes: torch.Tensor, ncols: int, denom, col_denom, seg_off: torch.Tensor, n_seg: int,
+          cell_label: torch.Tensor, n_labels: int):
+    """K6.  votes float32 [>=ncols, M].  Returns (auroc float64 [n_labels, ncols], n_pos int32 [n_labels])."""
+    M = int(votes.shape[1])
+    dev = votes.device
+    out = torch.empty((n_labels, ncols), dtype=torch.float64, device=dev)
+    n_pos = torch.empty((n_labels,), dtype=torch.int32, device=dev)
+    wbytes = _lib.auroc_workspace_bytes(ncols, M)
+    ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+    _lib.call("mn_auroc", votes, int(votes.stride(0)), ncols, denom, col_denom, seg_off, n_seg, cell_label,
+              n_labels, M, out, n_pos, ws, wbytes)
+    return out, n_pos
+
+
+def one_vs_best(votes, ncols, denom, col_denom, seg_lab_off, n_seg, lab_row_off, cell_label, n_labels, auc):
+    """K7.  Returns float64 [n_labels, ncols], NaN except two cells per (study, column)."""
+    out = torch.full((n_labels, ncols), float("nan"), dtype=torch.float64, device=votes.device)
+    _lib.call("mn_one_vs_best", votes, int(votes.stride(0)), ncols, denom, col_denom, seg_lab_off, n_seg,
+              lab_row_off, cell_label, n_labels, auc, out)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# pipelines
+# ---------------------------------------------------------------------------
+def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_train, train_study, n_train_studies,
+                             ndn: bool, ovb: bool):
+    """predict_and_score (MetaNeighborUS.py:310-387) for all test studies at once.
+    C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids."""
+    dev = rc.d_hi.device
+    n_b = n_train + (n_train_studies if ndn else 0)
+    b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
+    addend = n_valid[:n_b].contiguous() if ndn else None
+    out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
+    denom = out[n_train:] if ndn else None
+    col_denom = train_study if ndn else None
+    kept = rc.inv_norm > 0
+    cell_label = torch.where(kept, _i32(lay.cell_label), torch.full_like(_i32(lay.cell_label), -1))
+    n_lab = len(lay.row_labels)
+    n_seg = len(lay.studies)
+    seg_off = _i32(lay.seg_off)
+    auc, n_pos = auroc(out, n_train, denom, col_denom, seg_off, n_seg, cell_label, n_lab)
+    res = auc
+    if ovb:
+        res = one_vs_best(out, n_train, denom, col_denom, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
+                          cell_label, n_lab, auc)
+    return res, auc, n_pos
+
+
+def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
+    """metaNeighborUS_fast.  X: numpy / torch float32 [N, G] (input cell order).
+    Returns dict(table [L, L] rows = test labels, cols = train labels (both row order),
+    auroc (one-vs-rest table), n_pos [L], flags uint8 [N] in device row order)."""
+    Xd = to_device(X, torch.float32)
+    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
+    L, S = len(lay.row_labels), len(lay.studies)
+    C, n_valid = centroids(rc, _i32(lay.lab_row_off), L, extra_rows=S)
+    train_study = _i32(lay.label_study)
+    if ndn:
+        group_sum_into(C, n_valid, L, train_study, S, rc.G)
+    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, L, train_study, S, ndn, ovb)
+    return dict(table=res.cpu().numpy(), auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(),
+                flags=rc.flags.cpu().numpy())
+
+
+def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.ndarray, model_study: np.ndarray,
+                  n_model_studies: int, ndn=True, ovb=False):
+    """MetaNeighborUS_from_trained.  model_centroids float [L_train, G] (rows = model
+    columns), model_n [L_train], model_study int [L_train]."""
+    Xd = to_device(X, torch.float32)
+    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
+    Lt = int(model_centroids.shape[0])
+    C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=Xd.device)
+    C[:Lt, :rc.G] = to_device(np.asarray(model_centroids, np.float32))
+    n_valid = torch.zeros((Lt + n_model_studies,), dtype=torch.float32, device=Xd.device)
+    n_valid[:Lt] = to_device(np.asarray(model_n, np.float32))
+    train_study = _i32(model_study)
+    if ndn:
+        group_sum_into(C, n_valid, Lt, train_study, n_model_studies, rc.G)
+    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, Lt, train_study, n_model_studies, ndn, ovb)
+    return dict(table=res.cpu().numpy(), auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(),
+                flags=rc.flags.cpu().numpy())
+
+
+def train_model(X, lay: LabelLayout):
+    """trainModel: returns dict(centroids float32 [L, G], n_cells [L], flags [N] device row order)."""
+    Xd = to_device(X, torch.float32)
+    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=1)
+    L = len(lay.row_labels)
+    C, n_valid = centroids(rc, _i32(lay.lab_row_off), L)
+    return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=rc.flags.cpu().numpy())
+
+
+def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAULT_NBINS, row_range=None):
+    """K4/K5: two tensor-core passes over the (never stored) cell x cell network.
+    Returns (votes uint64-as-int64 [N, L], degree [N], hist [nbins], lut)."""
+    dev = rc.d_hi.device
+    N = rc.M
+    r0, r1 = (0, N) if row_range is None else row_range
+    hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
+    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, r0, r1, rc.G, nbins, hist)
+    lut = torch.empty((nbins + 1,), dtype=torch.int32, device=dev)
+    _lib.call("mn_corr_lut", hist, nbins, N, lut)
+    votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
+    degree = torch.zeros((N,), dtype=torch.int64, device=dev)
+    _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, r0, r1, rc.G, nbins, lut, label, L,
+              votes, degree)
+    return votes, degree, hist, lut
+
+
+def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):
+    """metaNeighborUS_default.  Returns dict(auroc [L, L] rows = TEST labels, cols = TRAIN
+    labels, both in row order -- the caller transposes / reorders, MetaNeighborUS.py:213)."""
+    Xd = to_device(X, torch.float32)
+    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
+    L, S = len(lay.row_labels), len(lay.studies)
+    cell_label = _i32(lay.cell_label)
+    votes, degree, hist, _ = corr_network_votes(rc, cell_label, L, nbins)
+    vmat = torch.empty((L, rc.M), dtype=torch.float32, device=Xd.device)
+    _lib.call("mn_votes_finalize", votes, degree, cell_label, rc.M, L, int(bool(ndn)), vmat, rc.M)
+    auc, n_pos = auroc(vmat, L, None, None, _i32(lay.seg_off), S, cell_label, L)
+    return dict(auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(), flags=rc.flags.cpu().numpy(),
+                hist_total=int(hist.sum().item()))
+
+
+# ---- supervised ------------------------------------------------------------
+def supervised_prepare(X, lay: LabelLayout):
+    """Upload the shared expression matrix once (MetaNeighbor.py:80-83)."""
+    return to_device(X, torch.float32), _i32(lay.perm)
+
+
+def supervised_geneset(Xd, perm_dev, cols: np.ndarray, lay: LabelLayout, n_types: int, ndn=True, fast=False,
+                       nbins=DEFAULT_NBINS):
+    """One gene set.  ``lay`` is the layout of JOINT labels study*K + type (all S*K ids,
+    empty ranges allowed).  Returns float64 [S*K, K] AUROC table (rows = joint test labels)."""
+    S = len(lay.studies)
+    K = n_types
+    col_index = _i32(cols)
+    rc = rank_normalize(Xd, row_index=perm_dev, col_index=col_index, drop_mode=1 if fast else 0)
+    dev = Xd.device
+    cell_label = _i32(lay.cell_label)
+    cell_study = _i32(lay.cell_study)
+    vmat = torch.empty((K, rc.M), dtype=torch.float32, device=dev)
+    if fast:
+        C, n_valid = centroids(rc, _i32(lay.lab_row_off), S * K)
+        b_hi, b_lo, inv_scale = split_f16(C, rc.G)
+        out = votes_fast(rc, b_hi, b_lo, inv_scale, None, S * K)
+        _lib.call("mn_loso_finalize", out, rc.M, 0, None, n_valid, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
+        kept = rc.inv_norm > 0
+        test_label = torch.where(kept, cell_label, torch.full_like(cell_label, -1))
+    else:
+        votes, degree, _, _ = corr_network_votes(rc, cell_label, S * K, nbins)
+        _lib.call("mn_loso_finalize", votes, S * K, 1, degree, None, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
+        test_label = cell_label
+    auc, _ = auroc(vmat, K, None, None, _i32(lay.seg_off), S, test_label, S * K)
+    return auc

@@ -1,0 +1,132 @@
+"""Host-side label logic of the hot path (mirrors reference pymn/utils.py:9-32,
+78-119): joined ``study|celltype`` labels, their sorted order (the column order
+``pd.get_dummies`` / ``np.unique`` give the reference), and the cell
+permutation that makes studies and labels contiguous row ranges on the device.
+Pure NumPy on integer codes -- no per-cell Python string work beyond one
+``np.unique`` per obs column.
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def join_labels(x, y, replace_bar=False):
+    """'$STUDY|$CELLTYPE' (reference utils.py:78-102).  Vectorised; kept public
+    because the reference re-exports it (pymn/__init__.py:18)."""
+    x = np.asarray(x, dtype=object)
+    y = np.asarray(y, dtype=object)
+    if replace_bar:
+        warnings.warn("Replacing any | with a . in study column values")
+        x = np.array([str(v).replace("|", ".") for v in x], dtype=object)
+    return np.array([str(a) + "|" + str(b) for a, b in zip(x, y)], dtype=object)
+
+
+def _factorize_sorted(vec):
+    """Sorted unique values (Python / code-point order, as np.unique on object
+    or str arrays) and int64 codes."""
+    vec = np.asarray(vec)
+    if vec.dtype.kind in "OUS":
+        as_str = np.array([v if isinstance(v, str) else str(v) for v in vec.tolist()], dtype=object)
+        uniq, codes = np.unique(as_str, return_inverse=True)
+        return np.asarray(uniq, dtype=object), codes.astype(np.int64)
+    uniq, codes = np.unique(vec, return_inverse=True)
+    return np.array([str(v) for v in uniq.tolist()], dtype=object), codes.astype(np.int64)
+
+
+@dataclass
+class LabelLayout:
+    """Device row layout: cells sorted by (study, joined label).
+
+    ``row_labels``  joined labels in table row order (for each study in sorted
+                    order, that study's labels sorted -- MetaNeighborUS.py:356,375)
+    ``perm``        int32[N]: device row i holds input cell perm[i]
+    ``cell_label``  int32[N]: row-order label id of device row i
+    ``cell_study``  int32[N]: study index of device row i
+    ``seg_off``     int32[S+1]: study t owns device rows [seg_off[t], seg_off[t+1])
+    ``lab_row_off`` int32[L+1]: label c owns device rows [lab_row_off[c], lab_row_off[c+1])
+    ``seg_lab_off`` int32[S+1]: study t owns labels [seg_lab_off[t], seg_lab_off[t+1])
+    ``label_study`` int32[L]: study index of each label
+    ``sorted_pos``  int64[L]: position of each row-order label in the globally
+                    sorted label list (np.unique(study_ct), utils.py:30)
+    """
+    studies: np.ndarray
+    row_labels: np.ndarray
+    perm: np.ndarray
+    cell_label: np.ndarray
+    cell_study: np.ndarray
+    seg_off: np.ndarray
+    lab_row_off: np.ndarray
+    seg_lab_off: np.ndarray
+    label_study: np.ndarray
+    sorted_pos: np.ndarray
+
+
+def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
+    st_uniq, st_codes = _factorize_sorted(study)
+    ct_uniq, ct_codes = _factorize_sorted(ctype)
+    n_ct = len(ct_uniq)
+    pair = st_codes * n_ct + ct_codes
+    pair_uniq, pair_codes = np.unique(pair, return_inverse=True)
+    st_of = pair_uniq // n_ct
+    st_names = [s.replace("|", ".") for s in st_uniq.tolist()] if replace_bar else st_uniq.tolist()
+    if replace_bar:
+        warnings.warn("Replacing any | with a . in study column values")
+    names = np.array([st_names[s] + "|" + ct_uniq[c] for s, c in zip(st_of.tolist(), (pair_uniq % n_ct).tolist())],
+                     dtype=object)
+    # row order: study (sorted) major, joined label (sorted as a string) minor
+    order = sorted(range(len(names)), key=lambda i: (int(st_of[i]), names[i]))
+    order = np.asarray(order, dtype=np.int64)
+    rank_of_pair = np.empty(len(names), np.int64)
+    rank_of_pair[order] = np.arange(len(names))
+    cell_label = rank_of_pair[pair_codes]
+    perm = np.argsort(cell_label, kind="stable")
+    row_labels = names[order]
+    label_study = st_of[order].astype(np.int32)
+    n_lab = len(names)
+    counts = np.bincount(cell_label, minlength=n_lab)
+    lab_row_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    n_st = len(st_uniq)
+    seg_lab_off = np.searchsorted(label_study, np.arange(n_st + 1)).astype(np.int32)
+    seg_off = lab_row_off[seg_lab_off].astype(np.int32)
+    glob = sorted(range(n_lab), key=lambda i: row_labels[i])
+    sorted_pos = np.empty(n_lab, np.int64)
+    sorted_pos[np.asarray(glob, dtype=np.int64)] = np.arange(n_lab)
+    return LabelLayout(studies=st_uniq, row_labels=row_labels, perm=perm.astype(np.int32),
+                       cell_label=cell_label[perm].astype(np.int32),
+                       cell_study=label_study[cell_label[perm]].astype(np.int32),
+                       seg_off=seg_off, lab_row_off=lab_row_off, seg_lab_off=seg_lab_off,
+                       label_study=label_study, sorted_pos=sorted_pos)
+
+
+def joint_layout(study, ctype):
+    """Layout for the supervised paths: label id = study * K + type over ALL
+    S*K combinations (empty ranges allowed), cells sorted by that id.
+    Returns (LabelLayout, cell-type names [K])."""
+    st_uniq, st_codes = _factorize_sorted(study)
+    ct_uniq, ct_codes = _factorize_sorted(ctype)
+    S, K = len(st_uniq), len(ct_uniq)
+    joint = st_codes * K + ct_codes
+    perm = np.argsort(joint, kind="stable")
+    counts = np.bincount(joint, minlength=S * K)
+    lab_row_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    seg_lab_off = (np.arange(S + 1) * K).astype(np.int32)
+    seg_off = lab_row_off[seg_lab_off].astype(np.int32)
+    names = np.array([f"{s}|{c}" for s in st_uniq.tolist() for c in ct_uniq.tolist()], dtype=object)
+    lay = LabelLayout(studies=st_uniq, row_labels=names, perm=perm.astype(np.int32),
+                      cell_label=joint[perm].astype(np.int32), cell_study=st_codes[perm].astype(np.int32),
+                      seg_off=seg_off, lab_row_off=lab_row_off, seg_lab_off=seg_lab_off,
+                      label_study=np.repeat(np.arange(S), K).astype(np.int32),
+                      sorted_pos=np.arange(S * K, dtype=np.int64))
+    return lay, ct_uniq
+
+
+def to_dense_f32(X) -> np.ndarray:
+    """Dense C-contiguous float32 cells x genes (the reference densifies at
+    utils.py:136-139; CSR ingestion on device is SURVEY section 8f 'next')."""
+    from scipy import sparse
+    if sparse.issparse(X):
+        X = X.toarray()
+    return np.ascontiguousarray(np.asarray(X), dtype=np.float32)

@@ -1,0 +1,260 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (pymn_b200._lib.call).
+
+Integer / index work (2*rank, histogram counts) must be bit-exact; floating
+point is held to the stated tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases as C
+from oracle import mn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from pymn_b200 import engine
+    return engine
+
+
+def _rand_matrix(rng, n, g, kind):
+    if kind == "counts":
+        x = rng.poisson(rng.gamma(0.5, 2.0, size=(1, g)), size=(n, g)).astype(np.float32)
+    elif kind == "dense":
+        x = rng.normal(size=(n, g)).astype(np.float32)
+    elif kind == "ties":
+        x = rng.integers(-2, 3, size=(n, g)).astype(np.float32)
+    else:
+        raise ValueError(kind)
+    return x
+
+
+@pytest.mark.parametrize("n,g,kind", [
+    (64, 257, "counts"), (33, 2000, "counts"), (17, 3000, "counts"), (40, 50, "ties"), (9, 1, "counts"),
+    (21, 2, "ties"), (30, 1000, "dense"), (12, 4096, "dense"), (25, 777, "ties"), (5, 16384, "counts"),
+])
+def test_rank_normalize_bit_exact(eng, n, g, kind):
+    rng = np.random.default_rng(n * 100003 + g)
+    x = _rand_matrix(rng, n, g, kind)
+    x[0] = 0.0                                   # zero-variance cell
+    if n > 3:
+        x[3] = 7.0                               # constant non-zero cell
+    rc = eng.rank_normalize(eng.to_device(x), want_xnorm=True, want_rank2=True)
+    torch.cuda.synchronize()
+    ref2 = O.rank2_rows(x)
+    got2 = rc.rank2.cpu().numpy()
+    assert np.array_equal(got2, ref2), "2*rank differs"
+    d = ref2 - (g + 1)
+    hi = rc.d_hi.cpu().numpy().astype(np.float64)[:, :g]
+    lo = rc.d_lo.cpu().numpy().astype(np.float64)[:, :g] if rc.d_lo is not None else 0.0
+    flags = rc.flags.cpu().numpy()
+    keep = (flags & 4) == 0
+    assert np.array_equal((hi + lo)[keep], d[keep].astype(np.float64)), "fp16 planes are not the exact integers"
+    assert np.all((hi + lo)[~keep] == 0)
+    assert np.all(rc.d_hi.cpu().numpy()[:, g:] == 0), "padding columns must be zero"
+    ss = (d.astype(np.float64) ** 2).sum(axis=1)
+    assert np.array_equal((flags & 1) != 0, ss == 0)
+    inv = rc.inv_norm.cpu().numpy()
+    assert np.all(inv[~keep] == 0)
+    np.testing.assert_allclose(inv[keep], 1.0 / np.sqrt(ss[keep]), rtol=1e-6)
+    ref = O.normalize_cells(x)
+    got = rc.xnorm.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref), initial=0.0) < 2e-7      # float32 rounding of a float64 result
+
+
+def test_rank_normalize_golden_and_gather(eng):
+    spec, inp, ref = C.load_case("normalize")
+    x = inp["X"]
+    rc = eng.rank_normalize(eng.to_device(x), want_xnorm=True, want_rank2=True)
+    assert np.array_equal(rc.rank2.cpu().numpy(), ref["rank2"])
+    np.testing.assert_allclose(rc.xnorm.cpu().numpy(), ref["xnorm"], atol=2e-7, rtol=0)
+    # row / column gathers
+    rng = np.random.default_rng(5)
+    rows = rng.permutation(x.shape[0])[:40].astype(np.int32)
+    cols = np.sort(rng.choice(x.shape[1], size=91, replace=False)).astype(np.int32)
+    rc2 = eng.rank_normalize(eng.to_device(x), row_index=eng._i32(rows), col_index=eng._i32(cols), want_rank2=True)
+    assert np.array_equal(rc2.rank2.cpu().numpy(), O.rank2_rows(x[np.ix_(rows, cols)]))
+
+
+def test_drop_mode_row_sum(eng):
+    x = np.array([[0, 0, 0, 0], [1, 2, 0, 0], [-3, 1, 1, 0], [2, 2, 2, 2]], dtype=np.float32)
+    rc = eng.rank_normalize(eng.to_device(x), drop_mode=1)
+    f = rc.flags.cpu().numpy()
+    assert list(f & 1) == [1, 0, 0, 1]          # zero variance
+    assert list((f >> 1) & 1) == [1, 0, 1, 0]   # sum <= 0
+    assert list((f >> 2) & 1) == [1, 0, 1, 1]   # dropped
+
+
+def _planes(rc, g):
+    hi = rc.d_hi.cpu().numpy().astype(np.float64)[:, :g]
+    if rc.d_lo is not None:
+        hi = hi + rc.d_lo.cpu().numpy().astype(np.float64)[:, :g]
+    return hi
+
+
+@pytest.mark.parametrize("n,g,L", [(500, 130, 7), (300, 2500, 3)])
+def test_centroids_and_group_sum(eng, n, g, L):
+    rng = np.random.default_rng(1)
+    x = _rand_matrix(rng, n, g, "counts")
+    x[5] = 0
+    rc = eng.rank_normalize(eng.to_device(x))
+    cuts = np.sort(rng.choice(np.arange(1, n), size=L - 1, replace=False))
+    row_off = np.concatenate([[0], cuts, [n]]).astype(np.int32)
+    Cd, nv = eng.centroids(rc, eng._i32(row_off), L, extra_rows=2)
+    group = (np.arange(L) % 2).astype(np.int32)
+    eng.group_sum_into(Cd, nv, L, eng._i32(group), 2, g)
+    xn = _planes(rc, g) * rc.inv_norm.cpu().numpy().astype(np.float64)[:, None]
+    ref = np.stack([xn[row_off[l]:row_off[l + 1]].sum(axis=0) for l in range(L)])
+    got = Cd.cpu().numpy()[:, :g]
+    np.testing.assert_allclose(got[:L], ref, atol=2e-6, rtol=1e-6)
+    kept = (rc.inv_norm.cpu().numpy() > 0)
+    assert np.array_equal(nv.cpu().numpy()[:L], [kept[row_off[l]:row_off[l + 1]].sum() for l in range(L)])
+    for q in range(2):
+        np.testing.assert_allclose(got[L + q], got[:L][group == q].sum(axis=0), atol=1e-5, rtol=1e-6)
+        assert nv.cpu().numpy()[L + q] == nv.cpu().numpy()[:L][group == q].sum()
+
+
+@pytest.mark.parametrize("m,nn,g", [(300, 42, 120), (1000, 200, 2500), (129, 257, 64), (5000, 13, 2000),
+                                    (4097, 128, 333)])
+def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
+    """tcgen05 GEMM vs float64 NumPy on the very same fp16 planes, and vs the CUDA-core debug kernel."""
+    rng = np.random.default_rng(m + nn + g)
+    x = _rand_matrix(rng, m, g, "counts")
+    rc = eng.rank_normalize(eng.to_device(x))
+    cent = rng.normal(size=(nn, g)).astype(np.float32) * rng.uniform(0.01, 50, size=(nn, 1)).astype(np.float32)
+    Cd = torch.zeros((nn, rc.ldd), dtype=torch.float32, device="cuda")
+    Cd[:, :g] = eng.to_device(cent)
+    b_hi, b_lo, inv_scale = eng.split_f16(Cd, g)
+    addend = eng.to_device(rng.uniform(0, 100, size=nn).astype(np.float32))
+    out = eng.votes_fast(rc, b_hi, b_lo, inv_scale, addend, nn)
+    dbg = eng.votes_fast(rc, b_hi, b_lo, inv_scale, addend, nn, debug_simt=True)
+    torch.cuda.synchronize()
+    a = _planes(rc, g)
+    b = (b_hi.cpu().numpy().astype(np.float64) + b_lo.cpu().numpy().astype(np.float64))[:, :g]
+    ref = (a @ b.T) * rc.inv_norm.cpu().numpy().astype(np.float64)[:, None] * inv_scale.cpu().numpy().astype(np.float64)[None, :]
+    ref = ref + addend.cpu().numpy().astype(np.float64)[None, :]
+    got = out.cpu().numpy().T.astype(np.float64)
+    scale = np.abs(ref - addend.cpu().numpy()[None, :]).max() + 1e-30
+    assert np.abs(dbg.cpu().numpy().T - ref).max() / scale < 1e-6
+    err = np.abs(got - ref).max() / scale
+    assert err < 2e-6, f"tcgen05 votes differ: rel err {err:.3e}"
+    # the split itself reproduces the float32 centroids to ~2^-22
+    np.testing.assert_allclose(b * inv_scale.cpu().numpy().astype(np.float64)[:, None], cent, rtol=0,
+                               atol=np.abs(cent).max(axis=1, keepdims=True).max() * 2.0 ** -21)
+
+
+@pytest.mark.parametrize("n_seg,seg_n,ncols,n_labels,ties", [
+    (1, 1000, 5, 4, False), (3, 2500, 9, 12, True), (2, 9000, 3, 6, False), (1, 37, 2, 2, True), (2, 5000, 4, 300, True),
+])
+def test_auroc_kernel_matches_oracle(eng, n_seg, seg_n, ncols, n_labels, ties):
+    rng = np.random.default_rng(seg_n + ncols)
+    M = n_seg * seg_n
+    votes = rng.normal(size=(ncols, M)).astype(np.float32)
+    if ties:
+        votes = np.round(votes, 1)
+        votes[0, : seg_n // 2] = 0.25                      # one giant tie run
+        if ncols > 1:
+            votes[1, :] = 1.0                              # a fully tied column
+    denom = rng.uniform(0.5, 2.0, size=(2, M)).astype(np.float32)
+    col_denom = (np.arange(ncols) % 2).astype(np.int32)
+    col_denom[-1] = -1
+    per_seg = n_labels // n_seg
+    lab = np.concatenate([np.sort(rng.integers(0, per_seg, size=seg_n)) + s * per_seg for s in range(n_seg)]).astype(np.int32)
+    excl = rng.random(M) < 0.05
+    lab_dev = np.where(excl, -1, lab).astype(np.int32)
+    seg_off = (np.arange(n_seg + 1) * seg_n).astype(np.int32)
+    auc, n_pos = eng.auroc(eng.to_device(votes), ncols, eng.to_device(denom), eng._i32(col_denom), eng._i32(seg_off),
+                           n_seg, eng._i32(lab_dev), n_labels)
+    torch.cuda.synchronize()
+    got = auc.cpu().numpy()
+    ref = np.full((n_labels, ncols), np.nan)
+    for s in range(n_seg):
+        sl = slice(s * seg_n, (s + 1) * seg_n)
+        keep = ~excl[sl]
+        key = votes[:, sl].copy()
+        for c in range(ncols):
+            if col_denom[c] >= 0:
+                key[c] = key[c] / denom[col_denom[c], sl]              # float32 division, as on the device
+        present, codes = O.encode(lab[sl][keep])
+        roc, _, _ = O.compute_aurocs(key[:, keep].T.astype(np.float64), codes, len(present))
+        ref[np.asarray(present, dtype=int)] = roc
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref), initial=0) == 0.0, "rank sums are integers: AUROC must be bit-identical"
+    cnt = np.bincount(lab[~excl], minlength=n_labels)
+    assert np.array_equal(n_pos.cpu().numpy(), cnt)
+
+
+def test_one_vs_best_kernel_matches_oracle(eng):
+    rng = np.random.default_rng(3)
+    n_seg, per_seg, ncols = 2, 7, 11
+    sizes = rng.integers(20, 120, size=n_seg * per_seg)
+    lab = np.repeat(np.arange(n_seg * per_seg), sizes).astype(np.int32)
+    M = lab.shape[0]
+    centers = rng.normal(size=(ncols, n_seg * per_seg))
+    votes = (centers[:, lab] + rng.normal(size=(ncols, M))).astype(np.float32)
+    votes = np.round(votes, 2)
+    lab_row_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    seg_lab_off = (np.arange(n_seg + 1) * per_seg).astype(np.int32)
+    seg_off = lab_row_off[seg_lab_off]
+    vd = eng.to_device(votes)
+    auc, _ = eng.auroc(vd, ncols, None, None, eng._i32(seg_off), n_seg, eng._i32(lab), n_seg * per_seg)
+    out = eng.one_vs_best(vd, ncols, None, None, eng._i32(seg_lab_off), n_seg, eng._i32(lab_row_off), eng._i32(lab),
+                          n_seg * per_seg, auc)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for s in range(n_seg):
+        sl = slice(seg_off[s], seg_off[s + 1])
+        codes = lab[sl] - s * per_seg
+        roc, _, _ = O.compute_aurocs(votes[:, sl].T.astype(np.float64), codes, per_seg)
+        ref = O.one_vs_best(votes[:, sl].T.astype(np.float64), codes, roc)
+        blk = got[s * per_seg:(s + 1) * per_seg]
+        assert np.array_equal(np.isnan(blk), np.isnan(ref))
+        assert np.nanmax(np.abs(blk - ref)) == 0.0
+
+
+@pytest.mark.parametrize("n,g", [(700, 96), (1500, 300), (640, 2100)])
+def test_corr_hist_and_votes(eng, n, g):
+    """Pass 1 counts every pair i<j exactly once into the right bin; pass 2's integer vote
+    sums equal the LUT-mapped network computed on the host from the same rho values."""
+    rng = np.random.default_rng(n + g)
+    x, s, c = __import__("pymn_b200.synth", fromlist=["make_counts"]).make_counts(n + g, 2, n // 2, g, 4)
+    x[7] = 0                                                # a dropped cell
+    rc = eng.rank_normalize(eng.to_device(x))
+    L = 5
+    label = rng.integers(0, L, size=n).astype(np.int32)
+    nb = 4096
+    votes, degree, hist, lut = eng.corr_network_votes(rc, eng._i32(label), L, nbins=nb)
+    torch.cuda.synchronize()
+    d = _planes(rc, g)
+    inv = rc.inv_norm.cpu().numpy()
+    kept = inv > 0
+    acc = (d @ d.T).astype(np.float32)                      # exact integers < 2^24? not always -> compare with slack
+    pos = np.float32(0.5 * nb)
+    binpos = (acc * (inv[:, None] * pos)).astype(np.float32) * inv[None, :] + pos
+    b = np.clip(np.floor(binpos).astype(np.int64), 0, nb - 1)
+    iu = np.triu_indices(n, 1)
+    ok = kept[iu[0]] & kept[iu[1]]
+    ref_hist = np.bincount(b[iu][ok], minlength=nb)
+    got_hist = hist.cpu().numpy()
+    m = int(kept.sum())
+    assert got_hist.sum() == m * (m - 1) // 2, "every kept pair exactly once"
+    # FP32 accumulation order may move a value across a bin edge: allow a handful of +-1 neighbours
+    assert np.abs(got_hist - ref_hist).sum() <= max(4, 2e-4 * ref_hist.sum())
+    lut_h = lut.cpu().numpy().astype(np.int64)
+    assert np.all(np.diff(lut_h) >= 0) and lut_h[0] == 0 and lut_h[-1] <= (1 << 30)
+    frac = np.clip(binpos - b, 0, 1).astype(np.float32)
+    w = lut_h[b] + np.floor(frac * (lut_h[b + 1] - lut_h[b]).astype(np.float32)).astype(np.int64)
+    w[~kept, :] = 0
+    w[:, ~kept] = 0
+    np.fill_diagonal(w, 0)
+    ref_deg = w.sum(axis=1)
+    ref_votes = np.stack([w[:, label == l].sum(axis=1) for l in range(L)], axis=1)
+    gd = degree.cpu().numpy()
+    gv = votes.cpu().numpy()
+    assert np.array_equal(gv.sum(axis=1), gd), "votes over all labels add up to the node degree (exact integers)"
+    rel = np.abs(gd - ref_deg).max() / ref_deg.max()
+    assert rel < 1e-5, f"node degree off by {rel:.2e}"
+    assert np.abs(gv - ref_votes).max() / ref_votes.max() < 1e-5

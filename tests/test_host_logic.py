@@ -1,0 +1,110 @@
+"""CPU tests: host-side label logic, the C-ABI library surface, API argument checks."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import mn_oracle as O
+from pymn_b200 import _lib
+from pymn_b200.utils import join_labels, joint_layout, label_layout
+from tests.helpers import ROOT, make_adata
+from oracle import cases as C
+
+
+def test_label_layout_matches_reference_order():
+    # "s1" vs "s10": '|' sorts after digits, so the joined-string order differs from the
+    # per-study order
+    study = np.array(["s10", "s1", "s2", "s1", "s10", "s2", "s1"], dtype=object)
+    ctype = np.array(["b", "a", "a", "b", "a", "c", "a"], dtype=object)
+    lay = label_layout(study, ctype)
+    assert list(lay.studies) == ["s1", "s10", "s2"]
+    assert list(lay.row_labels) == ["s1|a", "s1|b", "s10|a", "s10|b", "s2|a", "s2|c"]
+    # global order = sorted joined strings
+    glob = [lay.row_labels[i] for i in np.argsort(lay.sorted_pos)]
+    assert glob == sorted(lay.row_labels.tolist())
+    assert glob[0] == "s10|a"
+    # device rows are grouped by label, labels by study
+    assert np.all(np.diff(lay.cell_label) >= 0)
+    assert list(lay.seg_off) == [0, 3, 5, 7]
+    assert list(lay.seg_lab_off) == [0, 2, 4, 6]
+    joined = join_labels(study, ctype)
+    assert [lay.row_labels[c] for c in lay.cell_label] == list(joined[lay.perm])
+    # agrees with the oracle's encoding
+    uniq, _ = O.encode(O.join_labels(study, ctype))
+    assert list(uniq) == glob
+
+
+def test_joint_layout_has_all_combinations():
+    study = np.array(["a", "a", "b", "b", "b"], dtype=object)
+    ctype = np.array(["x", "y", "y", "y", "z"], dtype=object)
+    lay, names = joint_layout(study, ctype)
+    assert list(names) == ["x", "y", "z"]
+    assert len(lay.row_labels) == 6
+    assert list(lay.lab_row_off) == [0, 1, 2, 2, 2, 4, 5]
+    assert list(lay.seg_off) == [0, 2, 5]
+
+
+def test_join_labels_replace_bar_warns():
+    with pytest.warns(UserWarning):
+        out = join_labels(np.array(["a|b"], dtype=object), np.array(["t"], dtype=object), replace_bar=True)
+    assert out[0] == "a.b|t"
+
+
+def test_shared_library_exports_every_declared_symbol():
+    """include/pymn_b200.h, the ctypes table and the built library agree (no compute calls)."""
+    header = open(os.path.join(ROOT, "include", "pymn_b200.h")).read()
+    declared = set(re.findall(r"\b(mn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mn_stream_t", "mn_half_t"}
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert os.path.isfile(_lib.LIB_PATH), "build the library first: pymn_b200/csrc/build.sh"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported"
+    assert _lib.load().mn_abi_version() == 1
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import pymn_b200
+    spec, inp, _ = C.load_case("us_fast_ndn")
+    ad = make_adata(inp)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pymn_b200.MetaNeighborUS(ad, "study_id", "cell_type", fast_version=True, save_uns=False)
+
+
+def test_api_assertions_match_reference_messages():
+    import pymn_b200
+    spec, inp, _ = C.load_case("us_fast_ndn")
+    ad = make_adata(inp)
+    with pytest.raises(AssertionError, match="Study Col not in adata"):
+        pymn_b200.MetaNeighborUS(ad, "nope", "cell_type")
+    with pytest.raises(AssertionError, match="Cluster Col not in adata"):
+        pymn_b200.MetaNeighborUS(ad, "study_id", "nope")
+    with pytest.raises(AssertionError, match="must be in adata.var_keys"):
+        pymn_b200.MetaNeighborUS(ad, "study_id", "cell_type", var_genes="missing")
+    with pytest.raises(AssertionError, match="one_vs_best"):
+        pymn_b200.MetaNeighborUS(ad, "study_id", "cell_type", one_vs_best=True)
+    ad.obs["study_id"] = ad.obs["study_id"].astype("category")
+    with pytest.raises(AssertionError, match="category type"):
+        pymn_b200.MetaNeighborUS(ad, "study_id", "cell_type", fast_version=True)
+    one = make_adata(inp)
+    one.obs["study_id"] = "only"
+    with pytest.raises(AssertionError, match="Need more than 1 study"):
+        pymn_b200.MetaNeighborUS(one, "study_id", "cell_type", fast_version=True)
+    with pytest.raises(AssertionError, match="Study Col not in adata"):
+        pymn_b200.trainModel(ad, "nope", "cell_type")
+    gs = pd.DataFrame(np.ones((3, 1), int), index=["zz1", "zz2", "zz3"], columns=["s"])
+    with pytest.raises(AssertionError, match="No matching genes"):
+        pymn_b200.MetaNeighbor(make_adata(inp), "study_id", "cell_type", gs)
+
+
+def test_shard_and_gather_single_rank():
+    from pymn_b200.MetaNeighbor import gather_columns, shard_columns
+    assert list(shard_columns(7, 1, 3)) == [1, 4]
+    a = np.arange(6.0).reshape(2, 3)
+    assert gather_columns(a, 3, 0, 1) is a
