@@ -115,16 +115,20 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  * Both accumulate with integer atomics (exact, order-independent, so the
  * result is bit-identical for any tile schedule or GPU count).  The caller
  * zeroes hist / votes / degree.  label[j] < 0 excludes cell j as a voter.
+ * Multi-GPU: of the 128-row tiles of [row0, row1) a launch handles those with
+ * (tile index) % shard_world == shard_rank, so row tiles are dealt round-robin
+ * (balances the triangular pass 1); single GPU = (0, 1).
  */
 int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
-                 int64_t N, int64_t row0, int64_t row1, int32_t G, int32_t nbins, uint64_t* hist,
-                 mn_stream_t stream);
+                 int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
+                 int32_t G, int32_t nbins, uint64_t* hist, mn_stream_t stream);
 /* n_diag = number of diagonal entries (all cells, they tie at rho = 1 -- utils.py:72) */
 int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut /* [nbins+1] */,
                 mn_stream_t stream);
 int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
-                 int64_t N, int64_t row0, int64_t row1, int32_t G, int32_t nbins, const uint32_t* lut,
-                 const int32_t* label, int32_t L, uint64_t* votes, uint64_t* degree, mn_stream_t stream);
+                 int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
+                 int32_t G, int32_t nbins, const uint32_t* lut, const int32_t* label, int32_t L,
+                 uint64_t* votes, uint64_t* degree, mn_stream_t stream);
 
 /* votes uint64 [N, L] + degree uint64 [N] -> float32 column-major [L, ldo] vote matrix.
  * Adds the diagonal (W_ii = 1, utils.py:74) to votes[i, label[i]] and degree[i];

@@ -44,6 +44,7 @@ void count_launch(int n = 1);
 // order-preserving map float -> uint32 (ascending floats -> ascending keys)
 __device__ __forceinline__ uint32_t float_key(float v) {
     uint32_t u = __float_as_uint(v);
+    if (u == 0x80000000u) u = 0u;      // -0.0 ties with +0.0
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 

@@ -46,6 +46,7 @@ struct GemmParams {
     int b_sel[MAX_TERMS];
     int tri;          // 1: only tiles that contain some column index > row index
     int mt0, mt1;     // row-tile range handled by this launch
+    int mt_step;      // ... of which every mt_step-th, starting at mt0 (row tiles dealt round-robin to GPUs)
     int n_tiles;      // number of column tiles
     int stages;
     // epilogue
@@ -132,6 +133,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 columns of this thread's row: sum of the NCHAIN partial accumulators (chain c lives BN columns further)
+template <int BN, int NCHAIN>
+__device__ __forceinline__ void tmem_ld_chains(uint32_t taddr, int n_chains, uint32_t (&r)[32]) {
+    tmem_ld32(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 1; c < NCHAIN; ++c) {
+        if (c < n_chains) {
+            uint32_t t[32];
+            tmem_ld32(taddr + (uint32_t)(c * BN), t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
+        }
+    }
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: 8-row groups of 1024 bytes (SBO), LBO unused.
@@ -156,11 +173,11 @@ __device__ __forceinline__ float rho_binpos(float acc, float inv_i_half, float i
 
 // ------------------------------------------------------------------ tile schedule
 struct TileIter {
-    int mt, nt_rel, mt1, n_tiles, tri, bn;
+    int mt, nt_rel, mt1, n_tiles, tri, bn, mt_step;
     __device__ __forceinline__ int first_nt(int m) const { return tri ? (m * BM) / bn : 0; }
     __device__ __forceinline__ int len(int m) const { return n_tiles - first_nt(m); }
     __device__ __forceinline__ void init(const GemmParams& p, int bn_, int start) {
-        mt = p.mt0; mt1 = p.mt1; n_tiles = p.n_tiles; tri = p.tri; bn = bn_;
+        mt = p.mt0; mt1 = p.mt1; n_tiles = p.n_tiles; tri = p.tri; bn = bn_; mt_step = p.mt_step;
         nt_rel = 0;
         advance(start);
     }
@@ -168,7 +185,7 @@ struct TileIter {
         long long rem = (long long)nt_rel + step;
         while (mt < mt1 && rem >= len(mt)) {
             rem -= len(mt);
-            ++mt;
+            mt += mt_step;
         }
         nt_rel = (int)rem;
     }
@@ -177,7 +194,7 @@ struct TileIter {
 };
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int EPI>
+template <int BN, int EPI, int NCHAIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -186,7 +203,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = BN * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    // NCHAIN independent accumulators per tile (k-blocks dealt round-robin, summed in FP32 by the
+    // epilogue): the tensor core truncates when it adds into a long FP32 chain, so shorter chains
+    // cut the accumulation bias NCHAIN-fold.  Two tiles in flight when TMEM (512 columns) allows.
+    constexpr int ACC_COLS = NCHAIN * BN;
+    constexpr int ACC_STAGES = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+    constexpr int WANT_COLS = ACC_COLS * ACC_STAGES;
+    constexpr int TMEM_COLS = (WANT_COLS <= 32) ? 32 : (WANT_COLS <= 64) ? 64 : (WANT_COLS <= 128) ? 128 : (WANT_COLS <= 256) ? 256 : 512;
 
     // carve-up: [stages * STAGE_BYTES] operand ring (1024-aligned) | epilogue table | barriers etc.
     unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
@@ -274,8 +298,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             for (; it.valid(); it.advance(gridDim.x)) {
                 mbar_wait(&tempty_bar[a], aph ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
                 for (int i = 0; i < n_iters; ++i) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC_COLS + (i % NCHAIN) * BN);
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(ring + (size_t)s * STAGE_BYTES);
@@ -285,7 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance the start address by k * 16 elements * 2 B = 32 B = 2 (16-byte units)
                         tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                   (i > 0 || k > 0) ? 1u : 0u);
+                                   (i >= NCHAIN || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[s]);      // frees the smem slot once these MMAs retire
                     if (++s == p.stages) {
@@ -294,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     }
                 }
                 tc_commit(&tfull_bar[a]);          // accumulator complete -> epilogue
-                if (++a == 2) {
+                if (++a == ACC_STAGES) {
                     a = 0;
                     aph ^= 1u;
                 }
@@ -328,14 +352,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
             mbar_wait(&tfull_bar[a], aph);
             tc_fence_after();
-            const uint32_t t_base = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_base = tmem_base + (uint32_t)(a * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+            const int n_chains = n_iters < NCHAIN ? n_iters : NCHAIN;
 
             if (EPI == EPI_STORE) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t r[32];
-                    tmem_ld32(t_base + (uint32_t)c0, r);
-                    tmem_ld_wait();
+                    tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
                     if (row_ok) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
@@ -352,8 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t r[32];
-                    tmem_ld32(t_base + (uint32_t)c0, r);
-                    tmem_ld_wait();
+                    tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
                     if (inv_i > 0.f) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
@@ -377,8 +400,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t r[32];
-                    tmem_ld32(t_base + (uint32_t)c0, r);
-                    tmem_ld_wait();
+                    tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int lab = s_lab[c0 + c];           // warp-uniform
@@ -408,7 +430,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[a]);
-            if (++a == 2) {
+            if (++a == ACC_STAGES) {
                 a = 0;
                 aph ^= 1u;
             }
@@ -538,7 +560,7 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NCHAIN>
 static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, const __half* b_hi,
                        const __half* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -564,11 +586,11 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     }
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
-    auto kern = gemm_kernel<BN, EPI>;
+    auto kern = gemm_kernel<BN, EPI, NCHAIN>;
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // number of tiles
     long long tiles = 0;
-    for (int mt = p.mt0; mt < p.mt1; ++mt) tiles += p.n_tiles - (p.tri ? (mt * BM) / BN : 0);
+    for (int mt = p.mt0; mt < p.mt1; mt += p.mt_step) tiles += p.n_tiles - (p.tri ? (mt * BM) / BN : 0);
     if (tiles <= 0) return 0;
     int grid = sm_count();
     if (tiles < grid) grid = (int)tiles;
@@ -604,6 +626,7 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
     p.tri = 0;
     p.mt0 = 0;
     p.mt1 = (int)((M + BM - 1) / BM);
+    p.mt_step = 1;
     p.inv_a = inv_norm;
     p.inv_b = inv_scale;
     p.addend = addend;
@@ -614,9 +637,9 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
     const __half* bh = reinterpret_cast<const __half*>(b_hi);
     const __half* bl = reinterpret_cast<const __half*>(b_lo);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Nn <= 64) return launch_gemm<64, EPI_STORE>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
-    if (Nn <= 128) return launch_gemm<128, EPI_STORE>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
-    return launch_gemm<256, EPI_STORE>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
+    // BN <= 128 leaves room for 4 accumulator chains in TMEM (accuracy over tile width)
+    if (Nn <= 64) return launch_gemm<64, EPI_STORE, 4>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
+    return launch_gemm<128, EPI_STORE, 4>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
 }
 
 static int corr_terms(mn::GemmParams& p, bool has_lo) {
@@ -631,18 +654,21 @@ static int corr_terms(mn::GemmParams& p, bool has_lo) {
 }
 
 int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t N,
-                 int64_t row0, int64_t row1, int32_t G, int32_t nbins, uint64_t* hist, mn_stream_t stream) {
+                 int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world, int32_t G, int32_t nbins,
+                 uint64_t* hist, mn_stream_t stream) {
     using namespace mn;
     if (check_planes("mn_corr_hist", d_hi, ldd, G)) return 1;
     MN_CHECK_ARG(inv_norm && hist && N >= 1 && row0 >= 0 && row1 <= N && row0 < row1, "mn_corr_hist: bad arguments");
     MN_CHECK_ARG(nbins >= 256 && nbins <= 32768 && (nbins & (nbins - 1)) == 0, "mn_corr_hist: nbins must be a power of two in [256, 32768]");
     MN_CHECK_ARG((row0 % BM) == 0, "mn_corr_hist: row0 must be a multiple of %d", BM);
+    MN_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "mn_corr_hist: bad shard");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.n_terms = corr_terms(p, d_lo != nullptr);
     p.tri = 1;
-    p.mt0 = (int)(row0 / BM);
+    p.mt0 = (int)(row0 / BM) + shard_rank;
     p.mt1 = (int)((row1 + BM - 1) / BM);
+    p.mt_step = shard_world;
     p.inv_a = inv_norm;
     p.inv_b = inv_norm;
     p.nbins = nbins;
@@ -650,7 +676,7 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
     // rows beyond row1 inside the last tile belong to the next shard: mask them via M
-    return launch_gemm<128, EPI_HIST>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    return launch_gemm<128, EPI_HIST, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
 }
 
 int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut, mn_stream_t stream) {
@@ -662,20 +688,23 @@ int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* l
 }
 
 int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t N,
-                 int64_t row0, int64_t row1, int32_t G, int32_t nbins, const uint32_t* lut, const int32_t* label,
-                 int32_t L, uint64_t* votes, uint64_t* degree, mn_stream_t stream) {
+                 int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world, int32_t G, int32_t nbins,
+                 const uint32_t* lut, const int32_t* label, int32_t L, uint64_t* votes, uint64_t* degree,
+                 mn_stream_t stream) {
     using namespace mn;
     if (check_planes("mn_corr_vote", d_hi, ldd, G)) return 1;
     MN_CHECK_ARG(inv_norm && lut && label && votes && degree && N >= 1 && L >= 1 && row0 >= 0 && row1 <= N && row0 < row1,
                  "mn_corr_vote: bad arguments");
     MN_CHECK_ARG(nbins >= 256 && nbins <= 32768 && (nbins & (nbins - 1)) == 0, "mn_corr_vote: nbins must be a power of two in [256, 32768]");
     MN_CHECK_ARG((row0 % BM) == 0, "mn_corr_vote: row0 must be a multiple of %d", BM);
+    MN_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "mn_corr_vote: bad shard");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.n_terms = corr_terms(p, d_lo != nullptr);
     p.tri = 0;
-    p.mt0 = (int)(row0 / BM);
+    p.mt0 = (int)(row0 / BM) + shard_rank;
     p.mt1 = (int)((row1 + BM - 1) / BM);
+    p.mt_step = shard_world;
     p.inv_a = inv_norm;
     p.inv_b = inv_norm;
     p.nbins = nbins;
@@ -686,7 +715,7 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.degree = reinterpret_cast<unsigned long long*>(degree);
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
-    return launch_gemm<128, EPI_VOTE>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    return launch_gemm<128, EPI_VOTE, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
 }
 
 int mn_debug_votes_simt(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,

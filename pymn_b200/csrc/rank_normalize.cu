@@ -178,7 +178,7 @@ extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row
     int T = 256;
     if (G <= 64) T = 32; else if (G <= 256) T = 64; else if (G <= 1024) T = 128;
     static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 40 * 1024 && smem > configured) {
         MN_CUDA(cudaFuncSetAttribute(mn::rank_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }

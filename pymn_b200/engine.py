@@ -210,35 +210,111 @@ def train_model(X, lay: LabelLayout):
     return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=rc.flags.cpu().numpy())
 
 
-def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAULT_NBINS, row_range=None):
+def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAULT_NBINS, shard=(0, 1),
+                       reduce_fn=None):
     """K4/K5: two tensor-core passes over the (never stored) cell x cell network.
-    Returns (votes uint64-as-int64 [N, L], degree [N], hist [nbins], lut)."""
+    ``shard`` = (rank, world): this GPU handles every world-th 128-row tile; ``reduce_fn``
+    (an in-place sum all-reduce over ranks) is applied to the histogram before the LUT and
+    to votes / degree afterwards -- integer sums, so the result is bit-identical for any
+    world size.  Returns (votes uint64-as-int64 [N, L], degree [N], hist [nbins], lut)."""
     dev = rc.d_hi.device
     N = rc.M
-    r0, r1 = (0, N) if row_range is None else row_range
+    rank, world = shard
     hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
-    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, r0, r1, rc.G, nbins, hist)
+    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist)
+    if reduce_fn is not None:
+        reduce_fn(hist)
     lut = torch.empty((nbins + 1,), dtype=torch.int32, device=dev)
     _lib.call("mn_corr_lut", hist, nbins, N, lut)
     votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
     degree = torch.zeros((N,), dtype=torch.int64, device=dev)
-    _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, r0, r1, rc.G, nbins, lut, label, L,
-              votes, degree)
+    _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, lut,
+              label, L, votes, degree)
+    if reduce_fn is not None:
+        reduce_fn(votes)
+        reduce_fn(degree)
     return votes, degree, hist, lut
+
+
+def dist_shard():
+    """(rank, world, reduce_fn) for the row-tile sharding of the full-network path.
+    With torch.distributed initialised on >1 ranks (one process per GPU, NCCL) the two
+    tensor-core passes are split by row tile and the integer partials summed with
+    all-reduce; otherwise a single GPU does everything."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            def _sum(t):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return dist.get_rank(), dist.get_world_size(), _sum
+    except Exception:
+        pass
+    return 0, 1, None
+
+
+class StageTimer:
+    """CUDA-event timer per named stage on the current stream (bench.py's roofline numbers)."""
+
+    def __init__(self):
+        self.events = {}
+
+    def start(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.events.setdefault(name, []).append([ev, None])
+
+    def stop(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.events[name][-1][1] = ev
+
+    def mean_ms(self):
+        return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in self.events.items()}
+
+
+def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAULT_NBINS, shard=None, timer=None):
+    """Device-resident full-network pipeline: every argument already lives in HBM.
+    Returns (auroc float64 [L, L] rows = test labels, n_pos, flags, hist)."""
+    rank, world, reduce_fn = shard if shard is not None else dist_shard()
+    t = timer
+    if t: t.start("rank_normalize")
+    rc = rank_normalize(Xd, row_index=perm, drop_mode=0)
+    if t: t.stop("rank_normalize")
+    dev = Xd.device
+    N = rc.M
+    hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
+    if t: t.start("corr_hist")
+    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist)
+    if t: t.stop("corr_hist")
+    if reduce_fn is not None:
+        reduce_fn(hist)
+    lut = torch.empty((nbins + 1,), dtype=torch.int32, device=dev)
+    _lib.call("mn_corr_lut", hist, nbins, N, lut)
+    votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
+    degree = torch.zeros((N,), dtype=torch.int64, device=dev)
+    if t: t.start("corr_vote")
+    _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, lut,
+              cell_label, L, votes, degree)
+    if t: t.stop("corr_vote")
+    if reduce_fn is not None:
+        reduce_fn(votes)
+        reduce_fn(degree)
+    vmat = torch.empty((L, N), dtype=torch.float32, device=dev)
+    _lib.call("mn_votes_finalize", votes, degree, cell_label, N, L, int(bool(ndn)), vmat, N)
+    if t: t.start("auroc")
+    auc, n_pos = auroc(vmat, L, None, None, seg_off, S, cell_label, L)
+    if t: t.stop("auroc")
+    return auc, n_pos, rc.flags, hist
 
 
 def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):
     """metaNeighborUS_default.  Returns dict(auroc [L, L] rows = TEST labels, cols = TRAIN
     labels, both in row order -- the caller transposes / reorders, MetaNeighborUS.py:213)."""
     Xd = to_device(X, torch.float32)
-    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
     L, S = len(lay.row_labels), len(lay.studies)
-    cell_label = _i32(lay.cell_label)
-    votes, degree, hist, _ = corr_network_votes(rc, cell_label, L, nbins)
-    vmat = torch.empty((L, rc.M), dtype=torch.float32, device=Xd.device)
-    _lib.call("mn_votes_finalize", votes, degree, cell_label, rc.M, L, int(bool(ndn)), vmat, rc.M)
-    auc, n_pos = auroc(vmat, L, None, None, _i32(lay.seg_off), S, cell_label, L)
-    return dict(auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(), flags=rc.flags.cpu().numpy(),
+    auc, n_pos, flags, hist = us_default_device(Xd, _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off), L, S,
+                                                ndn, nbins)
+    return dict(auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(), flags=flags.cpu().numpy(),
                 hist_total=int(hist.sum().item()))
 
 

@@ -140,7 +140,8 @@ def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
     scale = np.abs(ref - addend.cpu().numpy()[None, :]).max() + 1e-30
     assert np.abs(dbg.cpu().numpy().T - ref).max() / scale < 1e-6
     err = np.abs(got - ref).max() / scale
-    assert err < 2e-6, f"tcgen05 votes differ: rel err {err:.3e}"
+    # FP32 accumulation of K ~ 2-3k exact products: IEEE sequential summation would give ~sqrt(K)*2^-24 = 3e-6
+    assert err < 4e-6, f"tcgen05 votes differ: rel err {err:.3e}"
     # the split itself reproduces the float32 centroids to ~2^-22
     np.testing.assert_allclose(b * inv_scale.cpu().numpy().astype(np.float64)[:, None], cent, rtol=0,
                                atol=np.abs(cent).max(axis=1, keepdims=True).max() * 2.0 ** -21)
@@ -233,7 +234,8 @@ def test_corr_hist_and_votes(eng, n, g):
     kept = inv > 0
     acc = (d @ d.T).astype(np.float32)                      # exact integers < 2^24? not always -> compare with slack
     pos = np.float32(0.5 * nb)
-    binpos = (acc * (inv[:, None] * pos)).astype(np.float32) * inv[None, :] + pos
+    t = (acc * (inv[:, None] * pos)).astype(np.float32)
+    binpos = (t.astype(np.float64) * inv[None, :].astype(np.float64) + np.float64(pos)).astype(np.float32)   # fmaf
     b = np.clip(np.floor(binpos).astype(np.int64), 0, nb - 1)
     iu = np.triu_indices(n, 1)
     ok = kept[iu[0]] & kept[iu[1]]
@@ -241,8 +243,11 @@ def test_corr_hist_and_votes(eng, n, g):
     got_hist = hist.cpu().numpy()
     m = int(kept.sum())
     assert got_hist.sum() == m * (m - 1) // 2, "every kept pair exactly once"
-    # FP32 accumulation order may move a value across a bin edge: allow a handful of +-1 neighbours
-    assert np.abs(got_hist - ref_hist).sum() <= max(4, 2e-4 * ref_hist.sum())
+    # FP32 accumulation in the tensor core may move a value across a bin edge into the
+    # neighbouring bin: the cumulative counts must agree up to a few such crossings
+    assert np.abs(np.cumsum(got_hist - ref_hist)).max() <= max(4, 2e-3 * ref_hist.sum())
+    if g * g * g < (1 << 24):
+        assert np.array_equal(got_hist, ref_hist), "all partial sums are exact integers < 2^24: histogram must be exact"
     lut_h = lut.cpu().numpy().astype(np.int64)
     assert np.all(np.diff(lut_h) >= 0) and lut_h[0] == 0 and lut_h[-1] <= (1 << 30)
     frac = np.clip(binpos - b, 0, 1).astype(np.float32)
