@@ -275,7 +275,7 @@ def run_ours(args):
     if rank == 0:
         peaks = _peaks()
         flops_hist = (N * (N - 1) / 2.0) * 2.0 * G / world
-        flops_vote = float(N) * N * 2.0 * G / world
+        flops_vote = flops_hist            # pass 2 also covers the upper triangle only (symmetric network)
         kern = {
             "corr_hist": {"ms": stage_ms["corr_hist"], "flop": flops_hist},
             "corr_vote": {"ms": stage_ms["corr_vote"], "flop": flops_vote},

@@ -110,11 +110,13 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  *                           over pairs i<j, i in [row0,row1), both cells kept
  * LUT   : mn_corr_lut    -- histogram -> fixed-point CDF table W = (rank-1)/max
  * Pass 2: mn_corr_vote   -- rho tiles again -> W via LUT -> integer vote sums
- *   votes  uint64 [N, L]  sum_j W_fix(rho_ij) [label(j)==l]   (W_fix = W * 2^30; j != i)
+ *   votes  uint64 [N, L]  sum_j W_fix(rho_ij) [label(j)==l]   (W_fix = W * 2^26; j != i)
  *   degree uint64 [N]     sum_j W_fix(rho_ij)                 (j != i)
  * Both accumulate with integer atomics (exact, order-independent, so the
  * result is bit-identical for any tile schedule or GPU count).  The caller
- * zeroes hist / votes / degree.  label[j] < 0 excludes cell j as a voter.
+ * zeroes hist / votes.  Every cell must carry a label in [0, L).  Pass 2 computes
+ * the upper triangle only (the network is symmetric) and adds each weight to both
+ * cells; `degree` is overwritten with the row sums of `votes`.
  * Multi-GPU: of the 128-row tiles of [row0, row1) a launch handles those with
  * (tile index) % shard_world == shard_rank, so row tiles are dealt round-robin
  * (balances the triangular pass 1); single GPU = (0, 1).

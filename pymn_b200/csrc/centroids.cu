@@ -105,13 +105,14 @@ __global__ void votes_finalize_kernel(const unsigned long long* __restrict__ vot
                                       float* __restrict__ out, int64_t ldo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const unsigned long long one = 1ull << 30;
+    const unsigned long long one = MN_W_ONE;
     const int li = label[i];
     const double deg = (double)(degree[i] + one);
+    const double inv_one = 1.0 / (double)MN_W_ONE;
     for (int l = 0; l < L; ++l) {
         unsigned long long v = votes[i * L + l];
         if (l == li) v += one;
-        const double x = ndn ? (double)v / deg : (double)v * (1.0 / 1073741824.0);
+        const double x = ndn ? (double)v / deg : (double)v * inv_one;
         out[(int64_t)l * ldo + i] = (float)x;
     }
 }
@@ -126,12 +127,13 @@ __global__ void loso_finalize_kernel(const void* __restrict__ in, int64_t ldi, i
     const int si = cell_study[i];
     if (is_fixed) {
         const unsigned long long* v = reinterpret_cast<const unsigned long long*>(in) + i * (int64_t)(S * K);
-        const double deg = (double)(degree[i] + (1ull << 30));
+        const double deg = (double)(degree[i] + MN_W_ONE);
+        const double inv_one = 1.0 / (double)MN_W_ONE;
         for (int k = 0; k < K; ++k) {
             unsigned long long acc = 0;
             for (int s = 0; s < S; ++s)
                 if (s != si) acc += v[s * K + k];
-            const double x = ndn ? (double)acc / deg : (double)acc * (1.0 / 1073741824.0);
+            const double x = ndn ? (double)acc / deg : (double)acc * inv_one;
             out[(int64_t)k * ldo + i] = (float)x;
         }
     } else {

@@ -11,6 +11,12 @@
 
 namespace mn {
 
+// Fixed-point scale of the rank-standardised network weight: W_fix = W * 2^MN_W_SHIFT, W in [0, 1].
+// 26 bits keep a warp-wide sum of 32 weights inside 32 bits (one REDUX.SUM) while the resolution
+// (1.5e-8) stays far below the LUT's interpolation error.
+constexpr int MN_W_SHIFT = 26;
+constexpr unsigned long long MN_W_ONE = 1ull << MN_W_SHIFT;
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 

@@ -23,6 +23,7 @@
 //   EPI_VOTE   pass 2: rho -> W via CDF LUT -> integer per-label vote sums + node degree
 //              (utils.py:46-51 + MetaNeighborUS.py:165-169); the N x N network never exists.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -31,7 +32,9 @@ namespace mn {
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int BK = 64;             // fp16 elements per k-block = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, each takes half of the tile columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_STAGES = 6;
 constexpr int MAX_TERMS = 4;
 
@@ -48,6 +51,7 @@ struct GemmParams {
     int mt0, mt1;     // row-tile range handled by this launch
     int mt_step;      // ... of which every mt_step-th, starting at mt0 (row tiles dealt round-robin to GPUs)
     int n_tiles;      // number of column tiles
+    int band;         // row tiles per L2 band of the tile schedule
     int stages;
     // epilogue
     const float* inv_a;      // [M] row scale (1/||d||), 0 = dropped cell
@@ -149,7 +153,7 @@ __device__ __forceinline__ void tmem_ld_chains(uint32_t taddr, int n_chains, uin
         }
     }
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // K-major, 128B-swizzled operand tile: 8-row groups of 1024 bytes (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -172,25 +176,63 @@ __device__ __forceinline__ float rho_binpos(float acc, float inv_i_half, float i
 }
 
 // ------------------------------------------------------------------ tile schedule
+// Row tiles owned by this launch: mt(k) = mt0 + k * mt_step, k in [0, n_my).  They are processed in
+// BANDS of `band` row tiles; inside a band the order is column tile outer, row tile inner.  The CTAs
+// of the persistent grid therefore work on a few neighbouring column tiles of one band at a time:
+// the band's A tiles (band * 128 rows) stay in L2 and every B tile is fetched from HBM once per band
+// instead of once per row tile.  In `tri` mode only tiles holding some column index > some row index
+// exist:  mt * BM < (nt + 1) * bn.
 struct TileIter {
-    int mt, nt_rel, mt1, n_tiles, tri, bn, mt_step;
-    __device__ __forceinline__ int first_nt(int m) const { return tri ? (m * BM) / bn : 0; }
-    __device__ __forceinline__ int len(int m) const { return n_tiles - first_nt(m); }
+    int mt0, mt_step, n_my, band, n_tiles, tri, bn;
+    int k0, nt_, r, mt;
+    bool ok;
+    __device__ __forceinline__ int mt_of(int k) const { return mt0 + k * mt_step; }
+    __device__ __forceinline__ int rows_in_band() const {
+        const int v = n_my - k0;
+        return v < band ? v : band;
+    }
+    __device__ __forceinline__ int first_nt_of_band() const { return tri ? (mt_of(k0) * BM) / bn : 0; }
+    __device__ __forceinline__ int col_len() const {
+        const int rows = rows_in_band();
+        if (!tri) return rows;
+        const int max_mt = ((nt_ + 1) * bn - 1) / BM;
+        if (max_mt < mt0) return 0;
+        const int cnt = (max_mt - mt0) / mt_step + 1 - k0;
+        return cnt < 0 ? 0 : (cnt < rows ? cnt : rows);
+    }
     __device__ __forceinline__ void init(const GemmParams& p, int bn_, int start) {
-        mt = p.mt0; mt1 = p.mt1; n_tiles = p.n_tiles; tri = p.tri; bn = bn_; mt_step = p.mt_step;
-        nt_rel = 0;
-        advance(start);
+        mt0 = p.mt0; mt_step = p.mt_step; band = p.band; n_tiles = p.n_tiles; tri = p.tri; bn = bn_;
+        n_my = p.mt1 > p.mt0 ? (p.mt1 - p.mt0 + p.mt_step - 1) / p.mt_step : 0;
+        k0 = 0; r = 0; mt = mt0;
+        ok = n_my > 0 && n_tiles > 0;
+        if (ok) {
+            nt_ = first_nt_of_band();
+            advance(start);
+        }
     }
     __device__ __forceinline__ void advance(int step) {
-        long long rem = (long long)nt_rel + step;
-        while (mt < mt1 && rem >= len(mt)) {
-            rem -= len(mt);
-            mt += mt_step;
+        if (!ok) return;
+        int rem = r + step;
+        for (;;) {
+            const int len = col_len();
+            if (rem < len) {
+                r = rem;
+                mt = mt_of(k0 + r);
+                return;
+            }
+            rem -= len;
+            if (++nt_ >= n_tiles) {
+                k0 += band;
+                if (k0 >= n_my) {
+                    ok = false;
+                    return;
+                }
+                nt_ = first_nt_of_band();
+            }
         }
-        nt_rel = (int)rem;
     }
-    __device__ __forceinline__ bool valid() const { return mt < mt1; }
-    __device__ __forceinline__ int nt() const { return first_nt(mt) + nt_rel; }
+    __device__ __forceinline__ bool valid() const { return ok; }
+    __device__ __forceinline__ int nt() const { return nt_; }
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -215,12 +257,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // carve-up: [stages * STAGE_BYTES] operand ring (1024-aligned) | epilogue table | barriers etc.
     unsigned char* ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
     unsigned char* tail = ring + (size_t)p.stages * STAGE_BYTES;
-    uint32_t* s_table = reinterpret_cast<uint32_t*>(tail);                 // hist [nbins] or lut [nbins+1]
-    const int table_words = (EPI == EPI_STORE) ? 0 : (p.nbins + 1 + 3) & ~3;
+    // hist: [nbins] counts + slot nbins (rho rounding above 1, folded into the top bin at the end)
+    //       + slot nbins+1 (sink for dropped cells);  lut: [nbins+1] edges + one pad entry
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(tail);
+    const int table_words = (EPI == EPI_STORE) ? 0 : (p.nbins + 2 + 3) & ~3;
     float* s_invb = reinterpret_cast<float*>(s_table + table_words);       // [BN]
     int32_t* s_lab = reinterpret_cast<int32_t*>(s_invb + BN);              // [BN]
-    float* s_add = reinterpret_cast<float*>(s_lab + BN);                   // [BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_add + BN);
+    float* s_add = reinterpret_cast<float*>(s_lab + BN);                   // [BN] (EPI_STORE) / flush masks (EPI_VOTE)
+    uint32_t* s_flush = reinterpret_cast<uint32_t*>(s_add);
+    uint32_t* s_colw = reinterpret_cast<uint32_t*>(s_add + BN);            // [EPI_WARPS][BN/2] column sums (EPI_VOTE)
+    int32_t* s_wlab = reinterpret_cast<int32_t*>(s_colw + EPI_WARPS * (BN / 2));   // [EPI_WARPS] row label of a uniform warp
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_wlab + EPI_WARPS);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + MAX_STAGES;
     uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
@@ -243,7 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 4);
+            mbar_init(&tempty_bar[a], EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -253,8 +300,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     if (EPI != EPI_STORE) {
         // hist starts at zero; lut is copied in
-        for (int i = threadIdx.x; i < p.nbins + 1; i += GEMM_THREADS)
-            s_table[i] = (EPI == EPI_VOTE) ? p.lut[i] : 0u;
+        for (int i = threadIdx.x; i < p.nbins + 2; i += GEMM_THREADS)
+            s_table[i] = (EPI == EPI_VOTE) ? p.lut[i < p.nbins ? i : p.nbins] : 0u;
     }
     tc_fence_before();
     __syncthreads();
@@ -326,9 +373,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
     } else {
         // ===================== epilogue warps =====================
+        const int ew = warp - 2;                      // 0..7
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
+        const int half = ew >> 2;                     // which half of the tile's columns
+        const int et = ew * 32 + lane;                // 0..255 among epilogue threads
         const int row_in_tile = q * 32 + lane;
+        constexpr int HALF_COLS = BN / 2;
+        const int cbeg = half * HALF_COLS;
         TileIter it;
         it.init(p, BN, blockIdx.x);
         int a = 0;
@@ -339,12 +390,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const int64_t m = m0 + row_in_tile;
             // stage per-column metadata of this tile
             epi_bar_sync();                           // previous tile's readers are done
-            for (int c = et; c < BN; c += 128) {
+            for (int c = et; c < BN; c += EPI_THREADS) {
                 const int64_t n = n0 + c;
                 const bool ok = n < p.N;
-                s_invb[c] = ok ? p.inv_b[n] : 0.f;
+                float ib = ok ? p.inv_b[n] : 0.f;
+                if (EPI == EPI_VOTE && !(ib > 0.f)) ib = __int_as_float(0x7fc00000);   // dropped / absent column: NaN
+                s_invb[c] = ib;
                 if (EPI == EPI_STORE) s_add[c] = (ok && p.addend) ? p.addend[n] : 0.f;
-                if (EPI == EPI_VOTE) s_lab[c] = ok ? p.label[n] : -1;
+                if (EPI == EPI_VOTE) {
+                    const int lab = ok ? p.label[n] : 0;
+                    s_lab[c] = lab;
+                    // a label run starts here (each half of the tile starts its own run)
+                    const bool brk = (c == 0) || (c == HALF_COLS) || !ok || (n >= 1 && p.label[n - 1] != lab);
+                    const unsigned msk = __ballot_sync(0xffffffffu, brk);
+                    if (lane == 0) s_flush[c >> 5] = msk;
+                }
             }
             epi_bar_sync();
             const bool row_ok = m < p.M;
@@ -354,10 +414,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)(a * ACC_COLS) + ((uint32_t)(q * 32) << 16);
             const int n_chains = n_iters < NCHAIN ? n_iters : NCHAIN;
+            // tile touches the diagonal: some column index <= some row index and vice versa
+            const bool diag_tile = (n0 <= m0 + BM - 1) && (n0 + BN - 1 >= m0);
 
             if (EPI == EPI_STORE) {
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
                     if (row_ok) {
@@ -371,62 +433,136 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 }
             } else if (EPI == EPI_HIST) {
                 const float inv_i_half = inv_i * half_bins;
-                const bool diag_tile = (n0 <= m0 + BM - 1);       // some column index <= some row index
-                const int maxbin = p.nbins - 1;
+                const unsigned top = (unsigned)p.nbins, sink = (unsigned)p.nbins + 1u;
+                const bool row_live = inv_i > 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
-                    if (inv_i > 0.f) {
+                    if (row_live) {
+                        if (!diag_tile) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float inv_j = s_invb[c0 + c];
-                            const bool use = (inv_j > 0.f) && (!diag_tile || (n0 + c0 + c > m));
-                            if (use) {
+                            for (int c = 0; c < 32; ++c) {
+                                const float inv_j = s_invb[c0 + c];
                                 const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
-                                int b = __float2int_rd(pos);
-                                b = min(max(b, 0), maxbin);
+                                unsigned b = min(__float2uint_rd(pos), top);
+                                b = (inv_j > 0.f) ? b : sink;
+                                atomicAdd(&s_table[b], 1u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const float inv_j = s_invb[c0 + c];
+                                const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                                unsigned b = min(__float2uint_rd(pos), top);
+                                b = (inv_j > 0.f && (n0 + c0 + c > m)) ? b : sink;
                                 atomicAdd(&s_table[b], 1u);
                             }
                         }
                     }
                 }
             } else {   // EPI_VOTE
-                const float inv_i_half = inv_i * half_bins;
-                const int maxbin = p.nbins - 1;
-                unsigned long long deg_acc = 0ull, run_acc = 0ull;
-                int cur_lab = -1;
+                // Every weight W_ij (j > i in `tri` mode: the network is symmetric, only the upper
+                // triangle is computed) is added to votes[i, label(j)] (row side: per-thread running
+                // sum over the label runs of the tile's columns) and, in `tri` mode, to
+                // votes[j, label(i)] (column side: one REDUX.SUM over the warp's 32 rows per column).
+                // Dropped cells carry NaN scales here: NaN propagates through the bin position, the
+                // float->uint conversions turn it into bin 0 / increment 0, and lut[0] == 0, so their
+                // weights vanish without a single predicate in the inner loop.
+                const float qnan = __int_as_float(0x7fc00000);
+                const float inv_i_half = (inv_i > 0.f) ? inv_i * half_bins : qnan;
+                const unsigned top = (unsigned)p.nbins;
+                const bool sym = p.tri != 0;
+                const int lab_i = p.label[row_ok ? m : p.M - 1];     // rows past the end carry zero weights
+                const unsigned gmask = __match_any_sync(0xffffffffu, lab_i);
+                const bool warp_uniform = (gmask == 0xffffffffu);
+                const bool grp_leader = (gmask & lanemask_lt()) == 0;
+                unsigned long long run_acc = 0ull;
+                int cur_lab = 0;
                 unsigned long long* vrow = p.votes + (row_ok ? m : 0) * (int64_t)p.L;
+                uint32_t* colw = s_colw + ew * HALF_COLS;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int lab = s_lab[c0 + c];           // warp-uniform
-                        if (lab != cur_lab) {
-                            if (run_acc && cur_lab >= 0) atomicAdd(vrow + cur_lab, run_acc);
+                    const unsigned brk = s_flush[c0 >> 5];
+                    uint32_t mycol = 0u;
+                    if (brk & 1u) {                              // warp-uniform: a label run starts with this chunk
+                        if (run_acc) {
+                            atomicAdd(vrow + cur_lab, run_acc);
                             run_acc = 0ull;
-                            cur_lab = lab;
                         }
-                        const float inv_j = s_invb[c0 + c];
-                        const bool use = (inv_i > 0.f) && (inv_j > 0.f) && (n0 + c0 + c != m);
-                        if (use) {
-                            const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
-                            int b = __float2int_rd(pos);
-                            b = min(max(b, 0), maxbin);
-                            const float frac = fminf(fmaxf(pos - (float)b, 0.f), 1.f);
+                        cur_lab = s_lab[c0];
+                    }
+                    if ((brk >> 1) == 0u && !diag_tile) {
+                        // fast path (almost every chunk): one label run, no diagonal -> branch-free
+                        uint32_t acc32 = 0u;                     // 32 weights <= 2^26 each fit 32 bits
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
+                            const unsigned b = min(__float2uint_rd(pos), top);
+                            const float frac = pos - (float)b;
                             const uint32_t lo = s_table[b], hi = s_table[b + 1];
                             const uint32_t w = lo + __float2uint_rd(frac * (float)(hi - lo));
-                            deg_acc += w;
-                            if (lab >= 0) run_acc += w;
+                            acc32 += w;
+                            r[c] = w;
+                        }
+                        run_acc += acc32;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (c > 0 && (brk & (1u << c))) {
+                                if (run_acc) {
+                                    atomicAdd(vrow + cur_lab, run_acc);
+                                    run_acc = 0ull;
+                                }
+                                cur_lab = s_lab[c0 + c];
+                            }
+                            const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
+                            const unsigned b = min(__float2uint_rd(pos), top);
+                            const float frac = pos - (float)b;
+                            const uint32_t lo = s_table[b], hi = s_table[b + 1];
+                            uint32_t w = lo + __float2uint_rd(frac * (float)(hi - lo));
+                            if (diag_tile) {
+                                const bool use = sym ? (n0 + c0 + c > m) : (n0 + c0 + c != m);
+                                w = use ? w : 0u;
+                            }
+                            run_acc += w;
+                            r[c] = w;
                         }
                     }
+                    if (sym && !warp_uniform) {                  // rows of several labels in one warp (rare)
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const uint32_t s = __reduce_add_sync(gmask, r[c]);
+                            if (grp_leader && s)
+                                atomicAdd(p.votes + (n0 + c0 + c) * (int64_t)p.L + lab_i, (unsigned long long)s);
+                        }
+                    }
+                    if (sym) {
+                        if (warp_uniform) {
+                            // 32 x 32 transpose-reduce: 31 shuffles leave in lane l the sum over the warp's
+                            // 32 rows of column c0 + l  (<= 32 * 2^26, fits 32 bits)
+#pragma unroll
+                            for (int off = 16; off >= 1; off >>= 1) {
+                                const bool up = (lane & off) != 0;
+#pragma unroll
+                                for (int c = 0; c < off; ++c) {
+                                    const uint32_t send = up ? r[c] : r[c + off];
+                                    const uint32_t keep = up ? r[c + off] : r[c];
+                                    r[c] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                                }
+                            }
+                            mycol = r[0];
+                        }
+                        colw[c0 - cbeg + lane] = mycol;
+                    }
                 }
-                if (run_acc && cur_lab >= 0) atomicAdd(vrow + cur_lab, run_acc);
-                if (deg_acc && row_ok) atomicAdd(p.degree + m, deg_acc);
+                if (run_acc) atomicAdd(vrow + cur_lab, run_acc);
+                if (sym && lane == 0) s_wlab[ew] = warp_uniform ? lab_i : -2;
             }
 
+            // the accumulator stage is drained: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[a]);
@@ -434,12 +570,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 a = 0;
                 aph ^= 1u;
             }
+
+            if (EPI == EPI_VOTE && p.tri != 0) {
+                // column side: merge the four row-quarter warps of each column half
+                epi_bar_sync();
+                const int lab0 = s_wlab[0];
+                bool tile_uniform = lab0 >= 0;
+#pragma unroll
+                for (int w8 = 1; w8 < EPI_WARPS; ++w8) tile_uniform = tile_uniform && (s_wlab[w8] == lab0);
+                if (tile_uniform) {
+                    for (int c = et; c < BN; c += EPI_THREADS) {
+                        const uint32_t* src = s_colw + (c / HALF_COLS) * 4 * HALF_COLS + (c % HALF_COLS);
+                        const unsigned long long sum = (unsigned long long)src[0] + src[HALF_COLS] +
+                                                       src[2 * HALF_COLS] + src[3 * HALF_COLS];
+                        if (sum) atomicAdd(p.votes + (n0 + c) * (int64_t)p.L + lab0, sum);
+                    }
+                } else {
+                    const int my_lab = s_wlab[ew];
+                    if (my_lab >= 0) {
+                        const uint32_t* src = s_colw + ew * HALF_COLS;
+                        for (int k = lane; k < HALF_COLS; k += 32) {
+                            const uint32_t v = src[k];
+                            if (v) atomicAdd(p.votes + (n0 + cbeg + k) * (int64_t)p.L + my_lab, (unsigned long long)v);
+                        }
+                    }
+                }
+            }
         }
         if (EPI == EPI_HIST) {
             epi_bar_sync();
-            for (int b = et; b < p.nbins; b += 128) {
+            for (int b = et; b <= p.nbins; b += EPI_THREADS) {
                 const uint32_t v = s_table[b];
-                if (v) atomicAdd(p.hist + b, (unsigned long long)v);
+                if (v) atomicAdd(p.hist + (b < p.nbins ? b : p.nbins - 1), (unsigned long long)v);
             }
         }
     }
@@ -457,7 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 // n_diag diagonal entries, which tie at the top (utils.py:72).  For a value at
 // fraction t of bin b:  rank - 1 ~= 2*(cum[b] + t*cnt[b]);  W = (rank-1)/top with
 // top = F - (n_diag-1)/2 - 1, F = 2*total + n_diag (utils.py:47-49).  lut[b] = W at the
-// lower edge of bin b in 2^30 fixed point, lut[nbins] = W at the upper edge.
+// lower edge of bin b in 2^MN_W_SHIFT fixed point, lut[nbins] = W at the upper edge.
 __global__ void corr_lut_kernel(const unsigned long long* __restrict__ hist, int nbins, long long n_diag,
                                 uint32_t* __restrict__ lut) {
     __shared__ unsigned long long s_part[1024];
@@ -482,13 +644,23 @@ __global__ void corr_lut_kernel(const unsigned long long* __restrict__ hist, int
     const double F = 2.0 * total + (double)n_diag;
     double top = F - ((double)n_diag - 1.0) * 0.5 - 1.0;
     if (!(top > 0.0)) top = 1.0;
-    const double scale = 1073741824.0 / top;
+    const double one = (double)MN_W_ONE;
+    const double scale = one / top;
     unsigned long long run = s_part[tid];
     for (int b = b0; b < b1; ++b) {
-        lut[b] = (uint32_t)fmin(1073741824.0, rint(2.0 * (double)run * scale));
+        lut[b] = (uint32_t)fmin(one, rint(2.0 * (double)run * scale));
         run += hist[b];
     }
-    if (tid == 0) lut[nbins] = (uint32_t)fmin(1073741824.0, rint(2.0 * total * scale));
+    if (tid == 0) lut[nbins] = (uint32_t)fmin(one, rint(2.0 * total * scale));
+}
+
+__global__ void vote_rowsum_kernel(const unsigned long long* __restrict__ votes, int64_t N, int L,
+                                   unsigned long long* __restrict__ degree) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    unsigned long long s = 0ull;
+    for (int l = 0; l < L; ++l) s += votes[i * L + l];
+    degree[i] = s;
 }
 
 // ------------------------------------------------------------------ debug reference (CUDA cores)
@@ -574,12 +746,22 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     p.N = N;
     p.k_blocks = (G + BK - 1) / BK;
     p.n_tiles = (int)((N + BN - 1) / BN);
+    if (p.band <= 0) p.band = 64;      // 64 x 128 rows x (G * 2 B) of A per band: 32 MB at G = 2000, L2-resident
+    if (const char* e = getenv("MN_GEMM_BAND")) {      // tuning knob
+        const int v = atoi(e);
+        if (v > 0) p.band = v;
+    }
     const size_t stage_bytes = (size_t)(BM + BN) * BK * 2;
-    const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 1 + 3) & ~3) * 4;
-    const size_t fixed = table + (size_t)BN * 12 + (2 * MAX_STAGES + 4) * 8 + 16;
+    const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 2 + 3) & ~3) * 4;
+    const size_t fixed = table + (size_t)BN * 12 + (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4 +
+                         (2 * MAX_STAGES + 4) * 8 + 16;
     const size_t budget = 232448 - 1024;          // 227 KB minus alignment slack
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (const char* e = getenv("MN_GEMM_STAGES")) {    // tuning knob (can only lower the depth)
+        const int v = atoi(e);
+        if (v >= 2 && v < stages) stages = v;
+    }
     if (stages < 2) {
         set_error("gemm: not enough shared memory for 2 pipeline stages (nbins=%d)", p.nbins);
         return 6;
@@ -676,6 +858,10 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
     // rows beyond row1 inside the last tile belong to the next shard: mask them via M
+    // 128 x 256 tiles move 25 % fewer operand bytes per flop through L2 (the measured bound); the table
+    // must then leave room for >= 2 pipeline stages of 48 KB, i.e. nbins <= 16384
+    if (nbins <= 16384 && !getenv("MN_GEMM_BN128"))
+        return launch_gemm<256, EPI_HIST, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     return launch_gemm<128, EPI_HIST, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
 }
 
@@ -701,7 +887,9 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.n_terms = corr_terms(p, d_lo != nullptr);
-    p.tri = 0;
+    // symmetric network: compute the upper triangle only and add every weight to both cells
+    // (MN_VOTE_FULL=1 computes all N^2 tiles instead; debugging aid)
+    p.tri = getenv("MN_VOTE_FULL") ? 0 : 1;
     p.mt0 = (int)(row0 / BM) + shard_rank;
     p.mt1 = (int)((row1 + BM - 1) / BM);
     p.mt_step = shard_world;
@@ -715,7 +903,16 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.degree = reinterpret_cast<unsigned long long*>(degree);
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
-    return launch_gemm<128, EPI_VOTE, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    int rc;
+    if (nbins <= 16384 && !getenv("MN_GEMM_BN128"))
+        rc = launch_gemm<256, EPI_VOTE, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    else
+        rc = launch_gemm<128, EPI_VOTE, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    if (rc) return rc;
+    // node degree = sum of a cell's votes over all labels (every voter carries a label)
+    vote_rowsum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.votes, N, L, p.degree);
+    MN_LAUNCH_CHECK();
+    return 0;
 }
 
 int mn_debug_votes_simt(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,

@@ -23,7 +23,10 @@ import torch
 from . import _lib
 from .utils import LabelLayout
 
-DEFAULT_NBINS = 32768      # CDF resolution of the global rank (bins over rho in [-1, 1])
+import os as _os
+
+# CDF resolution of the global rank (bins over rho in [-1, 1]); MN_NBINS is a tuning knob
+DEFAULT_NBINS = int(_os.environ.get("MN_NBINS", "16384"))
 
 
 def _dev():
