@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <limits.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pymn_b200.h"
@@ -19,6 +21,15 @@ constexpr unsigned long long MN_W_ONE = 1ull << MN_W_SHIFT;
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+
+// rank_warp.cu
+int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
+                     __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
+                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask);
+// rank_count.cu
+int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
+                      __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
+                      int32_t* rank2, int drop_mode, cudaStream_t st);
 
 #define MN_CHECK_ARG(cond, ...)              \
     do {                                     \

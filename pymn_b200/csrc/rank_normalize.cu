@@ -41,7 +41,8 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
                                       const int32_t* __restrict__ col_index, int64_t M, int G, int Pmax,
                                       __half* __restrict__ d_hi, __half* __restrict__ d_lo, int64_t ldd,
                                       float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
-                                      float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode) {
+                                      float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode,
+                                      int only_overflow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw);   // [Pmax]
     int* r2 = reinterpret_cast<int*>(skey + Pmax);            // [G]
@@ -53,6 +54,8 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
     const unsigned lt = lanemask_lt();
 
     for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+        // second stage of the warp-per-cell kernel: only rows it flagged as too dense (bit 3)
+        if (only_overflow && !(flags[row] & 8)) continue;
         const int64_t src = row_index ? (int64_t)row_index[row] : row;
         const float* x = X + src * ldx;
         if (tid == 0) {
@@ -173,6 +176,31 @@ extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row
     MN_CHECK_ARG(ldd >= G && (ldd % 8) == 0, "mn_rank_normalize: ldd=%lld must be >= G and a multiple of 8", (long long)ldd);
     MN_CHECK_ARG(G <= 2048 || d_lo, "mn_rank_normalize: G=%d > 2048 needs the d_lo plane", G);
     if (M <= 0) return 0;
+    // fast path: one warp per cell, register bitonic sort (rank_warp.cu); rows with more than 2048
+    // non-zeros (only possible for G > 2048) are flagged and redone below by the CTA-per-cell kernel
+    // Three stages, each a persistent grid; a later stage only touches the rows the earlier one flagged:
+    //   1. rank_count.cu   rows of small non-negative integers (counts): rank by counting, HBM-bound
+    //   2. rank_warp.cu    any other row (flag bit 4): one warp per cell, register bitonic sort
+    //   3. below           rows with more than 1024 non-zeros (flag bit 3): CTA per cell, shared-memory sort
+    int only_overflow = 0;
+    if (!getenv("MN_RANK_CTA")) {
+        __half* hi = reinterpret_cast<__half*>(d_hi);
+        __half* lo = reinterpret_cast<__half*>(d_lo);
+        cudaStream_t st = (cudaStream_t)stream;
+        int only_mask = 0;
+        if (!getenv("MN_RANK_NOCOUNT")) {
+            const int rc = mn::launch_rank_count(X, ldx, row_index, col_index, M, G, hi, lo, ldd, inv_norm, flags, xnorm,
+                                                 rank2, drop_mode, st);
+            if (rc) return rc;
+            only_mask = 16;
+        }
+        bool may_overflow = false;
+        const int rc = mn::launch_rank_warp(X, ldx, row_index, col_index, M, G, hi, lo, ldd, inv_norm, flags, xnorm, rank2,
+                                            drop_mode, st, &may_overflow, only_mask);
+        if (rc) return rc;
+        if (!may_overflow) return 0;
+        only_overflow = 1;
+    }
     const int Pmax = mn::next_pow2(G < 2 ? 2 : G);
     const size_t smem = (size_t)Pmax * 8 + (size_t)G * 4;
     int T = 256;
@@ -182,10 +210,11 @@ extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row
         MN_CUDA(cudaFuncSetAttribute(mn::rank_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int64_t grid = M < (int64_t)(1 << 30) ? M : (int64_t)(1 << 30);
+    int64_t grid = M < (int64_t)(1 << 30) ? M : (int64_t)(1 << 30);
+    if (only_overflow && grid > 1184) grid = 1184;      // a small persistent grid scans the flags for the few dense rows
     mn::rank_normalize_kernel<<<(unsigned)grid, T, smem, (cudaStream_t)stream>>>(
         X, ldx, row_index, col_index, M, G, Pmax, reinterpret_cast<__half*>(d_hi), reinterpret_cast<__half*>(d_lo),
-        ldd, inv_norm, flags, xnorm, rank2, drop_mode);
+        ldd, inv_norm, flags, xnorm, rank2, drop_mode, only_overflow);
     MN_LAUNCH_CHECK();
     return 0;
 }
