@@ -18,7 +18,7 @@ namespace mn {
 
 constexpr int AT = 512;                 // threads per CTA
 constexpr int ANW = AT / 32;            // warps
-constexpr int AITEMS = 4;               // keys per thread per tile
+constexpr int AITEMS = 8;               // keys per thread per tile
 constexpr int ATILE = AT * AITEMS;      // keys per tile
 
 __device__ __forceinline__ float vote_value(const float* __restrict__ v, const float* __restrict__ dn, int64_t i) {
@@ -100,18 +100,84 @@ auroc_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, const floa
     for (int i = tid; i < 4 * 256; i += AT) (&hist[0][0])[i] = 0u;
     __syncthreads();
 
-    // ---- pre-sweep: digit histograms of all four bytes + label counts -------
-    for (int i = tid; i < n; i += AT) {
-        const int lab = lab_in[i];
-        uint32_t key = 0xffffffffu;
-        if (lab >= 0) {
-            key = float_key(vote_value(v, dn, i));
-            atomicAdd(&cnt[lab], 1u);
+    // ---- sweep A: range of the kept keys.  Sorting (key - kmin) instead of key makes the high
+    // digits constant whenever the votes span less than 2^24 / 2^16 key values (they usually sit in
+    // one or two binades), and constant digits are skipped below: 3 radix passes instead of 4.
+    __shared__ uint32_t s_kmn[32], s_kmx[32];
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int i0 = 0; i0 < n; i0 += 4 * AT) {
+        float fv[4], fd[4];
+        int fl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                      // four independent loads in flight per thread
+            const int i = i0 + u * AT + tid;
+            fl[u] = i < n ? lab_in[i] : -1;
+            fv[u] = i < n ? v[i] : 0.f;
+            fd[u] = (dn && i < n) ? dn[i] : 1.f;
         }
-        atomicAdd(&hist[0][key & 255u], 1u);
-        atomicAdd(&hist[1][(key >> 8) & 255u], 1u);
-        atomicAdd(&hist[2][(key >> 16) & 255u], 1u);
-        atomicAdd(&hist[3][key >> 24], 1u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (fl[u] >= 0) {
+                const uint32_t k = float_key(dn ? __fdiv_rn(fv[u], fd[u]) : fv[u]);
+                kmin = min(kmin, k);
+                kmax = max(kmax, k);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) {
+        s_kmn[warp] = kmin;
+        s_kmx[warp] = kmax;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        kmin = (lane < ANW) ? s_kmn[lane] : 0xffffffffu;
+        kmax = (lane < ANW) ? s_kmx[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if (lane == 0) {
+            s_kmn[0] = kmin;
+            s_kmx[0] = kmax;
+        }
+    }
+    __syncthreads();
+    kmin = s_kmn[0];
+    kmax = s_kmx[0];
+    const uint32_t krange = (kmax >= kmin) ? (kmax - kmin) : 0u;
+    const uint32_t sentinel = (krange == 0xffffffffu) ? krange : krange + 1u;   // excluded cells sort last
+    if (kmax < kmin) kmin = 0u;
+
+    // ---- sweep B: digit histograms of all four bytes + label counts -------
+    for (int i0 = 0; i0 < n; i0 += 4 * AT) {
+        float fv[4], fd[4];
+        int fl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * AT + tid;
+            fl[u] = i < n ? lab_in[i] : -1;
+            fv[u] = i < n ? v[i] : 0.f;
+            fd[u] = (dn && i < n) ? dn[i] : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * AT + tid >= n) continue;          // past the end of the segment
+            uint32_t key = sentinel;
+            if (fl[u] >= 0) {
+                key = float_key(dn ? __fdiv_rn(fv[u], fd[u]) : fv[u]) - kmin;
+                atomicAdd(&cnt[fl[u]], 1u);
+            }
+            atomicAdd(&hist[0][key & 255u], 1u);
+            atomicAdd(&hist[1][(key >> 8) & 255u], 1u);
+            atomicAdd(&hist[2][(key >> 16) & 255u], 1u);
+            atomicAdd(&hist[3][key >> 24], 1u);
+        }
     }
     __syncthreads();
     if (tid < 4) s_flag[tid] = 1;     // 1 = pass needed
@@ -144,23 +210,37 @@ auroc_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, const floa
             uint16_t lab[AITEMS];
             int off[AITEMS];
             unsigned int* wc = wcnt[warp];
+            // all of the tile's loads first (independent, AITEMS in flight per thread) ...
+            if (ksrc) {
+#pragma unroll
+                for (int j = 0; j < AITEMS; ++j) {
+                    const int idx = t0 + warp * (32 * AITEMS) + j * 32 + lane;
+                    key[j] = idx < n ? ksrc[idx] : 0u;
+                    lab[j] = idx < n ? lsrc[idx] : (uint16_t)0;
+                }
+            } else {
+                float fv[AITEMS], fd[AITEMS];
+                int fl[AITEMS];
+#pragma unroll
+                for (int j = 0; j < AITEMS; ++j) {
+                    const int idx = t0 + warp * (32 * AITEMS) + j * 32 + lane;
+                    fv[j] = idx < n ? v[idx] : 0.f;
+                    fd[j] = (dn && idx < n) ? dn[idx] : 1.f;
+                    fl[j] = idx < n ? lab_in[idx] : -1;
+                }
+#pragma unroll
+                for (int j = 0; j < AITEMS; ++j) {
+                    const float val = dn ? __fdiv_rn(fv[j], fd[j]) : fv[j];
+                    key[j] = (fl[j] >= 0) ? float_key(val) - kmin : sentinel;
+                    lab[j] = (uint16_t)(fl[j] >= 0 ? fl[j] : 0xffff);
+                }
+            }
+            // ... then the stable in-warp ranking of their digits
 #pragma unroll
             for (int j = 0; j < AITEMS; ++j) {
                 const int idx = t0 + warp * (32 * AITEMS) + j * 32 + lane;
                 const bool in = idx < n;
-                key[j] = 0;
-                lab[j] = 0;
                 off[j] = -1;
-                if (in) {
-                    if (ksrc) {
-                        key[j] = ksrc[idx];
-                        lab[j] = lsrc[idx];
-                    } else {
-                        const int l = lab_in[idx];
-                        key[j] = (l >= 0) ? float_key(vote_value(v, dn, idx)) : 0xffffffffu;
-                        lab[j] = (uint16_t)(l >= 0 ? l : 0xffff);
-                    }
-                }
                 const unsigned active = __ballot_sync(0xffffffffu, in);
                 unsigned peers = 0, prior = 0;
                 const unsigned dig = (key[j] >> shift) & 255u;

@@ -27,13 +27,20 @@ def join_labels(x, y, replace_bar=False):
 def _factorize_sorted(vec):
     """Sorted unique values (Python / code-point order, as np.unique on object
     or str arrays) and int64 codes."""
+    import pandas as pd
     vec = np.asarray(vec)
+    # hash-factorise the N cells (O(N)), then sort only the handful of distinct values
+    codes, uniq = pd.factorize(vec, sort=False)
+    uniq = np.asarray(uniq)
     if vec.dtype.kind in "OUS":
-        as_str = np.array([v if isinstance(v, str) else str(v) for v in vec.tolist()], dtype=object)
-        uniq, codes = np.unique(as_str, return_inverse=True)
-        return np.asarray(uniq, dtype=object), codes.astype(np.int64)
-    uniq, codes = np.unique(vec, return_inverse=True)
-    return np.array([str(v) for v in uniq.tolist()], dtype=object), codes.astype(np.int64)
+        names = [v if isinstance(v, str) else str(v) for v in uniq.tolist()]
+        order = sorted(range(len(names)), key=lambda i: names[i])          # code-point order, as np.unique
+    else:
+        order = np.argsort(uniq, kind="stable").tolist()                      # numeric order, as np.unique
+        names = [str(v) for v in uniq.tolist()]
+    remap = np.empty(len(order), np.int64)
+    remap[np.asarray(order, dtype=np.int64)] = np.arange(len(order))
+    return np.array([names[i] for i in order], dtype=object), remap[codes]
 
 
 @dataclass
