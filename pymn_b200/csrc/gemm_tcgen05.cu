@@ -37,6 +37,7 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_STAGES = 6;
 constexpr int MAX_TERMS = 4;
+constexpr int TQ = 4;                     // depth of the tile-index queue of the dynamic scheduler
 
 enum { EPI_STORE = 0, EPI_HIST = 1, EPI_VOTE = 2 };
 
@@ -52,6 +53,9 @@ struct GemmParams {
     int mt_step;      // ... of which every mt_step-th, starting at mt0 (row tiles dealt round-robin to GPUs)
     int n_tiles;      // number of column tiles
     int band;         // row tiles per L2 band of the tile schedule
+    int dbg_skip_col; // experiment switch (MN_DBG_SKIP_COL): drop the column-side reductions (wrong results)
+    unsigned int* tile_counter;   // dynamic tile scheduler: next linear tile index (zeroed before the launch)
+    int total_tiles;
     int stages;
     // epilogue
     const float* inv_a;      // [M] row scale (1/||d||), 0 = dropped cell
@@ -152,6 +156,16 @@ __device__ __forceinline__ void tmem_ld_chains(uint32_t taddr, int n_chains, uin
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t[j]));
         }
     }
+}
+// 64-bit integer reduction to global memory whose L2 line is marked evict-first: the column-side vote
+// sums stream through the whole votes array once per band and must not push the operand tiles out of L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void red_add_u64_hint(unsigned long long* addr, unsigned long long val, uint64_t pol) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(addr), "l"(val), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
@@ -272,7 +286,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     uint64_t* empty_bar = bars + MAX_STAGES;
     uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
     uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+    uint64_t* qfull_bar = bars + 2 * MAX_STAGES + 4;                       // tile-index queue (dynamic scheduler)
+    uint64_t* qempty_bar = bars + 2 * MAX_STAGES + 4 + TQ;
+    int32_t* s_tileq = reinterpret_cast<int32_t*>(bars + 2 * MAX_STAGES + 4 + 2 * TQ);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_tileq + TQ);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_iters = p.n_terms * p.k_blocks;
@@ -291,6 +308,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], EPI_WARPS);
+        }
+        for (int qi = 0; qi < TQ; ++qi) {
+            mbar_init(&qfull_bar[qi], 1);
+            mbar_init(&qempty_bar[qi], 1 + EPI_WARPS);     // MMA thread + one lane of every epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -311,11 +332,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // Dynamic tile scheduler: the producer claims the next linear tile index with one atomicAdd and
+            // publishes it to the MMA and epilogue roles through a small shared-memory queue.  All CTAs
+            // therefore work inside one narrow window of the (band, column, row) order even when their
+            // speeds differ -- which keeps the band's operands in L2 (a static round-robin lets slow CTAs
+            // fall behind until the working set of in-flight column tiles exceeds L2).
             TileIter it;
-            it.init(p, BN, blockIdx.x);
-            int s = 0;
-            uint32_t ph = 0;
-            for (; it.valid(); it.advance(gridDim.x)) {
+            it.init(p, BN, 0);
+            int cur_tile = 0;
+            int s = 0, qs = 0;
+            uint32_t ph = 0, qph = 0;
+            for (;;) {
+                mbar_wait(&qempty_bar[qs], qph ^ 1u);
+                const unsigned int t = atomicAdd(p.tile_counter, 1u);
+                const int tile = (t < (unsigned int)p.total_tiles) ? (int)t : -1;
+                s_tileq[qs] = tile;
+                mbar_arrive(&qfull_bar[qs]);
+                if (++qs == TQ) {
+                    qs = 0;
+                    qph ^= 1u;
+                }
+                if (tile < 0) break;
+                it.advance(tile - cur_tile);
+                cur_tile = tile;
                 const int m0 = it.mt * BM, n0 = it.nt() * BN;
                 for (int term = 0; term < p.n_terms; ++term) {
                     const CUtensorMap* ma = p.a_sel[term] ? &tm_a_lo : &tm_a_hi;
@@ -338,11 +377,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BM, BN);
-            TileIter it;
-            it.init(p, BN, blockIdx.x);
-            int s = 0, a = 0;
-            uint32_t ph = 0, aph = 0;
-            for (; it.valid(); it.advance(gridDim.x)) {
+            int s = 0, a = 0, qs = 0;
+            uint32_t ph = 0, aph = 0, qph = 0;
+            for (;;) {
+                mbar_wait(&qfull_bar[qs], qph);
+                const int tile = s_tileq[qs];
+                mbar_arrive(&qempty_bar[qs]);
+                if (++qs == TQ) {
+                    qs = 0;
+                    qph ^= 1u;
+                }
+                if (tile < 0) break;
                 mbar_wait(&tempty_bar[a], aph ^ 1u);
                 tc_fence_after();
                 for (int i = 0; i < n_iters; ++i) {
@@ -381,11 +426,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         constexpr int HALF_COLS = BN / 2;
         const int cbeg = half * HALF_COLS;
         TileIter it;
-        it.init(p, BN, blockIdx.x);
-        int a = 0;
-        uint32_t aph = 0;
+        it.init(p, BN, 0);
+        int cur_tile = 0;
+        int a = 0, qs = 0;
+        uint32_t aph = 0, qph = 0;
         const float half_bins = 0.5f * (float)p.nbins;
-        for (; it.valid(); it.advance(gridDim.x)) {
+        const uint64_t pol_ef = l2_evict_first_policy();
+        for (;;) {
+            mbar_wait(&qfull_bar[qs], qph);
+            const int tile = s_tileq[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qempty_bar[qs]);
+            if (++qs == TQ) {
+                qs = 0;
+                qph ^= 1u;
+            }
+            if (tile < 0) break;
+            it.advance(tile - cur_tile);
+            cur_tile = tile;
             const int64_t m0 = (int64_t)it.mt * BM, n0 = (int64_t)it.nt() * BN;
             const int64_t m = m0 + row_in_tile;
             // stage per-column metadata of this tile
@@ -536,7 +594,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         for (int c = 0; c < 32; ++c) {
                             const uint32_t s = __reduce_add_sync(gmask, r[c]);
                             if (grp_leader && s)
-                                atomicAdd(p.votes + (n0 + c0 + c) * (int64_t)p.L + lab_i, (unsigned long long)s);
+                                red_add_u64_hint(p.votes + (n0 + c0 + c) * (int64_t)p.L + lab_i, (unsigned long long)s, pol_ef);
                         }
                     }
                     if (sym) {
@@ -583,7 +641,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         const uint32_t* src = s_colw + (c / HALF_COLS) * 4 * HALF_COLS + (c % HALF_COLS);
                         const unsigned long long sum = (unsigned long long)src[0] + src[HALF_COLS] +
                                                        src[2 * HALF_COLS] + src[3 * HALF_COLS];
-                        if (sum) atomicAdd(p.votes + (n0 + c) * (int64_t)p.L + lab0, sum);
+                        if (sum && !p.dbg_skip_col) red_add_u64_hint(p.votes + (n0 + c) * (int64_t)p.L + lab0, sum, pol_ef);
                     }
                 } else {
                     const int my_lab = s_wlab[ew];
@@ -591,7 +649,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         const uint32_t* src = s_colw + ew * HALF_COLS;
                         for (int k = lane; k < HALF_COLS; k += 32) {
                             const uint32_t v = src[k];
-                            if (v) atomicAdd(p.votes + (n0 + cbeg + k) * (int64_t)p.L + my_lab, (unsigned long long)v);
+                            if (v) red_add_u64_hint(p.votes + (n0 + cbeg + k) * (int64_t)p.L + my_lab, (unsigned long long)v, pol_ef);
                         }
                     }
                 }
@@ -754,7 +812,7 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     const size_t stage_bytes = (size_t)(BM + BN) * BK * 2;
     const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 2 + 3) & ~3) * 4;
     const size_t fixed = table + (size_t)BN * 12 + (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4 +
-                         (2 * MAX_STAGES + 4) * 8 + 16;
+                         (2 * MAX_STAGES + 4 + 2 * TQ) * 8 + TQ * 4 + 16;
     const size_t budget = 232448 - 1024;          // 227 KB minus alignment slack
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -776,6 +834,15 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     if (tiles <= 0) return 0;
     int grid = sm_count();
     if (tiles < grid) grid = (int)tiles;
+    // dynamic scheduler: one counter per launch out of a small rotating pool (launches on different
+    // streams may overlap), zeroed on the launch stream
+    static unsigned int* counters = nullptr;
+    static int next_counter = 0;
+    constexpr int N_COUNTERS = 64;
+    if (!counters) MN_CUDA(cudaMalloc(&counters, N_COUNTERS * sizeof(unsigned int)));
+    p.tile_counter = counters + (next_counter++ % N_COUNTERS);
+    p.total_tiles = (int)tiles;
+    MN_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), st));
     kern<<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
     MN_LAUNCH_CHECK();
     return 0;
@@ -890,6 +957,7 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     // symmetric network: compute the upper triangle only and add every weight to both cells
     // (MN_VOTE_FULL=1 computes all N^2 tiles instead; debugging aid)
     p.tri = getenv("MN_VOTE_FULL") ? 0 : 1;
+    p.dbg_skip_col = getenv("MN_DBG_SKIP_COL") ? 1 : 0;
     p.mt0 = (int)(row0 / BM) + shard_rank;
     p.mt1 = (int)((row1 + BM - 1) / BM);
     p.mt_step = shard_world;
