@@ -66,6 +66,16 @@ int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row_index, con
                       float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
                       int32_t drop_mode, mn_stream_t stream);
 
+/* Same, reading the expression matrix in CSR form (scipy.sparse.csr_matrix: indptr int64 [n_rows+1],
+ * indices int32 [nnz], data float32 [nnz]) -- the layout AnnData keeps X in.  Replaces the
+ * X.toarray() + rankdata of normalize_cells (utils.py:136-141): only the stored values cross
+ * PCIe / HBM (8 B per non-zero instead of 4 B per gene).  Implicit entries are zeros; explicit
+ * zeros are allowed; indices must be unique within a row.  No column sub-setting. */
+int mn_rank_normalize_csr(const int64_t* indptr, const int32_t* indices, const float* data,
+                          const int32_t* row_index, int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo,
+                          int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
+                          int32_t drop_mode, mn_stream_t stream);
+
 /* ---- K2: cluster centroids ----------------------------------------------
  * Replaces X_norm @ onehot (MetaNeighborUS.py:284, trainModel.py:43,
  * MetaNeighbor.py:170 inner product) and n_cells_per_cluster (:288).

@@ -11,7 +11,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, to_dense_f32
+from .utils import label_layout, prepare_matrix
 
 
 def _pvals(roc: np.ndarray, n_pos: np.ndarray, n_neg: np.ndarray) -> np.ndarray:
@@ -35,7 +35,7 @@ def metaNeighborUS_fast(X, S, C, node_degree_normalization, one_vs_best, compute
     S = np.asarray(S.values if hasattr(S, "values") else S, dtype=object)
     C = np.asarray(C.values if hasattr(C, "values") else C, dtype=object)
     lay = label_layout(S, C)
-    r = engine.us_fast(to_dense_f32(X), lay, bool(node_degree_normalization), bool(one_vs_best))
+    r = engine.us_fast(prepare_matrix(X), lay, bool(node_degree_normalization), bool(one_vs_best))
     keep = _keep_rows(r["n_pos"])        # labels whose cells were all zero-variance vanish (:273-281)
     labels = lay.row_labels[keep]
     tab = pd.DataFrame(r["table"][np.ix_(keep, keep)], index=labels, columns=labels)
@@ -59,7 +59,7 @@ def MetaNeighborUS_from_trained(trained_model, test_data, study_col, ct_col, nod
     n_cells = np.asarray(trained_model.iloc[0].values, dtype=np.float32)
     st_names = np.array([str(c).split("|")[0] for c in cols.values], dtype=object)    # :341-343
     st_uniq, st_codes = np.unique(st_names, return_inverse=True)
-    r = engine.us_pretrained(to_dense_f32(test_data), lay, cent, n_cells, st_codes.astype(np.int32), len(st_uniq),
+    r = engine.us_pretrained(prepare_matrix(test_data), lay, cent, n_cells, st_codes.astype(np.int32), len(st_uniq),
                              bool(node_degree_normalization), bool(one_vs_best))
     keep = _keep_rows(r["n_pos"])
     labels = lay.row_labels[keep]
@@ -79,7 +79,7 @@ def metaNeighborUS_default(adata, study_col, ct_col, node_degree_normalization, 
     S = np.asarray(adata.obs[study_col].values, dtype=object)
     C = np.asarray(adata.obs[ct_col].values, dtype=object)
     lay = label_layout(S, C)
-    r = engine.us_default(to_dense_f32(adata.X), lay, bool(node_degree_normalization))
+    r = engine.us_default(prepare_matrix(adata.X), lay, bool(node_degree_normalization))
     order = np.argsort(lay.sorted_pos)                       # row-order ids in globally sorted order
     labels = lay.row_labels[order]
     auc = r["auroc"][np.ix_(order, order)]                   # [test, train]

@@ -298,40 +298,45 @@ auroc_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, const floa
     } else if (n_valid > 0) {
         const uint32_t* ks = kb[cur];
         const uint16_t* ls = lb[cur];
-        // forward: first position of each tie run
-        int carry = 0;
-        for (int t0 = 0; t0 < n_valid; t0 += AT) {
-            const int p = t0 + tid;
-            const bool in = p < n_valid;
-            uint32_t k = 0;
-            int val = 0;
-            if (in) {
-                k = ks[p];
-                const bool is_start = (p == 0) || (ks[p - 1] != k);
-                val = is_start ? p : 0;
+        // Sorted keys -> 2*rank = first + last + 2 of the element's tie run.  Ties are rare among
+        // float votes, so every element just compares with its two neighbours; only a tied element
+        // binary-searches the ends of its run.  No block-wide communication: eight independent
+        // elements per thread keep the L2 loads in flight.
+        for (int t0 = 0; t0 < n_valid; t0 += 8 * AT) {
+            uint32_t k[8], kp[8], kn[8];
+            uint16_t lab8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = t0 + u * AT + tid;
+                const bool in = p < n_valid;
+                k[u] = in ? ks[p] : 0u;
+                kp[u] = (in && p > 0) ? ks[p - 1] : ~k[u];
+                kn[u] = (in && p + 1 < n_valid) ? ks[p + 1] : ~k[u];
+                lab8[u] = in ? ls[p] : (uint16_t)0;
             }
-            int tot;
-            int s = block_scan_max(val, s_warp, &tot);
-            s = max(s, carry);
-            carry = max(carry, tot);
-            if (in) acc_add(acc_lo, acc_hi, ls[p], (unsigned int)s);
-        }
-        // backward: last position of each tie run (max-scan of -position)
-        carry = INT_MIN;
-        for (int t0 = 0; t0 < n_valid; t0 += AT) {
-            const int q = t0 + tid;
-            const int p = n_valid - 1 - q;
-            const bool in = q < n_valid;
-            int val = INT_MIN;
-            if (in) {
-                const bool is_end = (p == n_valid - 1) || (ks[p + 1] != ks[p]);
-                val = is_end ? -p : INT_MIN;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = t0 + u * AT + tid;
+                if (p >= n_valid) continue;
+                int first = p, last = p;
+                if (kp[u] == k[u]) {                     // first position whose key >= k
+                    int lo = 0, hi = p - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (ks[mid] < k[u]) lo = mid + 1; else hi = mid;
+                    }
+                    first = lo;
+                }
+                if (kn[u] == k[u]) {                     // last position whose key <= k
+                    int lo = p + 1, hi = n_valid - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (ks[mid] > k[u]) hi = mid - 1; else lo = mid;
+                    }
+                    last = lo;
+                }
+                acc_add(acc_lo, acc_hi, lab8[u], (unsigned int)(first + last + 2));
             }
-            int tot;
-            int s = block_scan_max(val, s_warp, &tot);
-            s = max(s, carry);
-            carry = max(carry, tot);
-            if (in) acc_add(acc_lo, acc_hi, ls[p], (unsigned int)(-s + 2));
         }
         __syncthreads();
     }
@@ -500,6 +505,10 @@ int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom,
     mn::fill_f64_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(auroc, tot, nan(""));
     MN_LAUNCH_CHECK();
     if (n_pos) MN_CUDA(cudaMemsetAsync(n_pos, 0, sizeof(int32_t) * n_labels, st));
+    // experimental sample-sort kernel (auroc_ss.cu): same results, not faster yet (both ~11 G votes/s) -- opt-in
+    if (getenv("MN_AUROC_SS"))
+        return mn::launch_auroc_ss(votes, ldv, ncols, denom, col_denom, seg_off, n_seg, cell_label, n_labels, per, auroc,
+                                   n_pos, keys0, keys1, labs0, labs1, st);
     const size_t dyn = (size_t)n_labels * 12 + 16;
     static size_t configured = 0;
     if (dyn > 16 * 1024 && dyn > configured) {

@@ -19,17 +19,29 @@ namespace mn {
 constexpr int MN_W_SHIFT = 26;
 constexpr unsigned long long MN_W_ONE = 1ull << MN_W_SHIFT;
 
+// optional CSR view of the expression matrix (scipy.sparse.csr_matrix layout); indptr == nullptr = dense input
+struct CsrIn {
+    const int64_t* indptr;    // [n_rows + 1]
+    const int32_t* indices;   // [nnz] gene index of each stored value
+    const float* data;        // [nnz]
+};
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
 // rank_warp.cu
 int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                      __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask);
+                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr);
+// auroc_ss.cu
+int launch_auroc_ss(const float* votes, int64_t ldv, int ncols, const float* denom, const int32_t* col_denom,
+                    const int32_t* seg_off, int n_seg, const int32_t* cell_label, int n_labels, int64_t per,
+                    double* auroc, int32_t* n_pos, uint32_t* keys0, uint32_t* keys1, uint16_t* labs0, uint16_t* labs1,
+                    cudaStream_t st);
 // rank_count.cu
 int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                       __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                      int32_t* rank2, int drop_mode, cudaStream_t st);
+                      int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr);
 
 #define MN_CHECK_ARG(cond, ...)              \
     do {                                     \

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32)
 rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ row_index,
                   const int32_t* __restrict__ col_index, int64_t M, int G, int g_pad, __half* __restrict__ d_hi,
                   __half* __restrict__ d_lo, int64_t ldd, float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
-                  float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode) {
+                  float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode, CsrIn csr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t per_warp = (size_t)RC_HB * 4 + (size_t)g_pad * 2;
@@ -44,7 +44,36 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
         bool ok = true;
         int nnz = 0, maxv = 0;
         float ps = 0.f;
-        if (vec4) {
+        if (csr.indptr) {
+            // CSR row: only the stored values travel (8 B per non-zero instead of 4 B per gene)
+            for (int g2 = lane; g2 < (g_pad >> 1); g2 += 32) reinterpret_cast<uint32_t*>(vals)[g2] = 0u;
+            __syncwarp();
+            const int64_t e0 = csr.indptr[src], e1 = csr.indptr[src + 1];
+            for (int64_t eb = e0; eb < e1; eb += 128) {
+                float f[4];
+                int jj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t e = eb + u * 32 + lane;
+                    f[u] = e < e1 ? __ldg(csr.data + e) : 0.f;
+                    jj[u] = e < e1 ? __ldg(csr.indices + e) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (eb + u * 32 + lane >= e1) continue;
+                    int iv = __float2int_rz(f[u]);
+                    ok = ok && ((unsigned)iv < (unsigned)RC_HB) && ((float)iv == f[u]) && ((unsigned)jj[u] < (unsigned)G);
+                    iv = min(max(iv, 0), RC_HB - 1);
+                    if (iv > 0) {
+                        atomicAdd(&tab[iv], 1u);
+                        ++nnz;
+                        maxv = max(maxv, iv);
+                        vals[min(max(jj[u], 0), G - 1)] = (uint16_t)iv;
+                    }
+                    ps += f[u];
+                }
+            }
+        } else if (vec4) {
             const float4* x4 = reinterpret_cast<const float4*>(x);
             const int G4 = G >> 2;
             for (int base = 0; base < G4; base += 128) {
@@ -122,6 +151,8 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
         // ---- 2. histogram -> 2*rank table (bins 1..maxv) -------------------------------------------
         const int nzero = G - nnz;
         const uint32_t zero_r2 = (uint32_t)(nzero + 1);                 // no negatives on this path
+        const int c = G + 1;
+        unsigned long long ss = 0;
         int below = 0;                                                  // non-zeros smaller than the chunk
         for (int b0 = 1; b0 <= maxv; b0 += 32) {
             const int b = b0 + lane;
@@ -132,27 +163,21 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                 const int t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            if (b <= maxv) tab[b] = (uint32_t)(2 * (nzero + below + inc - cnt) + cnt + 1);
+            if (b <= maxv) {
+                const int r2 = 2 * (nzero + below + inc - cnt) + cnt + 1;
+                tab[b] = (uint32_t)r2;
+                const long long d = (long long)r2 - c;             // all cnt entries of this value share d
+                ss += (unsigned long long)(d * d) * (unsigned long long)cnt;
+            }
             below += __shfl_sync(0xffffffffu, inc, 31);
         }
         __syncwarp();
         // ---- 3. look up, centre, write ------------------------------------------------------------------
-        const int c = G + 1;
+        // the sum of squares comes from the histogram: sum_v cnt(v) * d(v)^2 (+ the zero block), no extra sweep
         // (an all-zero or constant row has a single tie block: d == 0 everywhere, detected through ss == 0)
-        unsigned long long ss = 0;
-        // first sweep: sum of squares only (needed for the drop decision before anything is written)
-        for (int g2 = lane; g2 < (g_pad >> 1); g2 += 32) {
-            const uint32_t pr = *reinterpret_cast<const uint32_t*>(vals + 2 * g2);
-            const int v0 = pr & 0xffffu, v1 = pr >> 16;
-            const int g = 2 * g2;
-            if (g < G) {
-                const long long d = (long long)(v0 ? tab[v0] : zero_r2) - c;
-                ss += (unsigned long long)(d * d);
-            }
-            if (g + 1 < G) {
-                const long long d = (long long)(v1 ? tab[v1] : zero_r2) - c;
-                ss += (unsigned long long)(d * d);
-            }
+        if (lane == 0) {
+            const long long d = (long long)zero_r2 - c;
+            ss += (unsigned long long)(d * d) * (unsigned long long)nzero;
         }
         ss = warp_sum(ss);
         const bool zv = (ss == 0ull);
@@ -201,7 +226,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
 
 int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                       __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                      int32_t* rank2, int drop_mode, cudaStream_t st) {
+                      int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr) {
     const int g_pad = (G + 7) & ~7;
     const size_t per_warp = (size_t)RC_HB * 4 + (size_t)g_pad * 2;
     const size_t smem = per_warp * RC_WARPS;
@@ -217,7 +242,7 @@ int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, con
     const int64_t max_blocks = (int64_t)sms * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     rank_count_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(X, ldx, row_index, col_index, M, G, g_pad, d_hi, d_lo,
-                                                                   ldd, inv_norm, flags, xnorm, rank2, drop_mode);
+                                                                   ldd, inv_norm, flags, xnorm, rank2, drop_mode, csr);
     MN_LAUNCH_CHECK();
     return 0;
 }

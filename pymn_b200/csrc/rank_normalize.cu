@@ -42,7 +42,7 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
                                       __half* __restrict__ d_hi, __half* __restrict__ d_lo, int64_t ldd,
                                       float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
                                       float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode,
-                                      int only_overflow) {
+                                      int only_overflow, CsrIn csr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw);   // [Pmax]
     int* r2 = reinterpret_cast<int*>(skey + Pmax);            // [G]
@@ -66,11 +66,23 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
 
         // ---- 1. load + compact non-zeros -----------------------------------
         double psum = 0.0;
-        for (int base = 0; base < G; base += T) {
-            const int g = base + tid;
-            const bool in = g < G;
+        const int64_t e0 = csr.indptr ? csr.indptr[src] : 0;
+        const int n_in = csr.indptr ? (int)(csr.indptr[src + 1] - e0) : G;      // stored values (CSR) or genes (dense)
+        for (int base = 0; base < n_in; base += T) {
+            const int q = base + tid;
+            bool in = q < n_in;
             float v = 0.f;
-            if (in) v = __ldg(x + (col_index ? col_index[g] : g));
+            int g = q;
+            if (in) {
+                if (csr.indptr) {
+                    v = __ldg(csr.data + e0 + q);
+                    g = __ldg(csr.indices + e0 + q);
+                    in = (unsigned)g < (unsigned)G;
+                    if (!in) v = 0.f;
+                } else {
+                    v = __ldg(x + (col_index ? col_index[g] : g));
+                }
+            }
             psum += (double)v;
             const bool nz = in && (v != 0.f);
             const bool ng = in && (v < 0.f);
@@ -167,11 +179,10 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
 
 }  // namespace mn
 
-extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index,
-                                 int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo, int64_t ldd,
-                                 float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
-                                 int32_t drop_mode, mn_stream_t stream) {
-    MN_CHECK_ARG(X && d_hi && inv_norm && flags, "mn_rank_normalize: null pointer");
+static int rank_dispatch(const float* X, int64_t ldx, mn::CsrIn csr, const int32_t* row_index, const int32_t* col_index,
+                         int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo, int64_t ldd, float* inv_norm,
+                         uint8_t* flags, float* xnorm, int32_t* rank2, int32_t drop_mode, mn_stream_t stream) {
+    MN_CHECK_ARG((X || csr.indptr) && d_hi && inv_norm && flags, "mn_rank_normalize: null pointer");
     MN_CHECK_ARG(G >= 1 && G <= 16384, "mn_rank_normalize: G=%d outside [1, 16384]", G);
     MN_CHECK_ARG(ldd >= G && (ldd % 8) == 0, "mn_rank_normalize: ldd=%lld must be >= G and a multiple of 8", (long long)ldd);
     MN_CHECK_ARG(G <= 2048 || d_lo, "mn_rank_normalize: G=%d > 2048 needs the d_lo plane", G);
@@ -190,13 +201,13 @@ extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row
         int only_mask = 0;
         if (!getenv("MN_RANK_NOCOUNT")) {
             const int rc = mn::launch_rank_count(X, ldx, row_index, col_index, M, G, hi, lo, ldd, inv_norm, flags, xnorm,
-                                                 rank2, drop_mode, st);
+                                                 rank2, drop_mode, st, csr);
             if (rc) return rc;
             only_mask = 16;
         }
         bool may_overflow = false;
         const int rc = mn::launch_rank_warp(X, ldx, row_index, col_index, M, G, hi, lo, ldd, inv_norm, flags, xnorm, rank2,
-                                            drop_mode, st, &may_overflow, only_mask);
+                                            drop_mode, st, &may_overflow, only_mask, csr);
         if (rc) return rc;
         if (!may_overflow) return 0;
         only_overflow = 1;
@@ -214,7 +225,27 @@ extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row
     if (only_overflow && grid > 1184) grid = 1184;      // a small persistent grid scans the flags for the few dense rows
     mn::rank_normalize_kernel<<<(unsigned)grid, T, smem, (cudaStream_t)stream>>>(
         X, ldx, row_index, col_index, M, G, Pmax, reinterpret_cast<__half*>(d_hi), reinterpret_cast<__half*>(d_lo),
-        ldd, inv_norm, flags, xnorm, rank2, drop_mode, only_overflow);
+        ldd, inv_norm, flags, xnorm, rank2, drop_mode, only_overflow, csr);
     MN_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mn_rank_normalize(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index,
+                                 int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo, int64_t ldd,
+                                 float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
+                                 int32_t drop_mode, mn_stream_t stream) {
+    MN_CHECK_ARG(X != nullptr, "mn_rank_normalize: null matrix");
+    mn::CsrIn none = {nullptr, nullptr, nullptr};
+    return rank_dispatch(X, ldx, none, row_index, col_index, M, G, d_hi, d_lo, ldd, inv_norm, flags, xnorm, rank2,
+                         drop_mode, stream);
+}
+
+extern "C" int mn_rank_normalize_csr(const int64_t* indptr, const int32_t* indices, const float* data,
+                                     const int32_t* row_index, int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo,
+                                     int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
+                                     int32_t drop_mode, mn_stream_t stream) {
+    MN_CHECK_ARG(indptr && indices && data, "mn_rank_normalize_csr: null CSR arrays");
+    mn::CsrIn csr = {indptr, indices, data};
+    return rank_dispatch(nullptr, 0, csr, row_index, nullptr, M, G, d_hi, d_lo, ldd, inv_norm, flags, xnorm, rank2,
+                         drop_mode, stream);
 }

@@ -162,7 +162,7 @@ rank_warp_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
                  const int32_t* __restrict__ col_index, int64_t M, int G, int cap, int g_pad,
                  __half* __restrict__ d_hi, __half* __restrict__ d_lo, int64_t ldd, float* __restrict__ inv_norm,
                  uint8_t* __restrict__ flags, float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode,
-                 int only_mask) {
+                 int only_mask, CsrIn csr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
@@ -180,7 +180,25 @@ rank_warp_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
         // ---- 1. load + compact -------------------------------------------------------------
         int nnz = 0, nneg = 0;
         float ps = 0.f;
-        if (vec4) {
+        if (csr.indptr) {
+            const int64_t e0 = csr.indptr[src], e1 = csr.indptr[src + 1];
+            for (int64_t eb = e0; eb < e1; eb += 128) {
+                float f[4];
+                int jj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t e = eb + u * 32 + lane;
+                    f[u] = e < e1 ? __ldg(csr.data + e) : 0.f;
+                    jj[u] = e < e1 ? __ldg(csr.indices + e) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool in = (eb + u * 32 + lane < e1) && ((unsigned)jj[u] < (unsigned)G);
+                    ps += in ? f[u] : 0.f;
+                    compact_one(f[u], in, jj[u], buf, cap, nnz, nneg, lt);
+                }
+            }
+        } else if (vec4) {
             const float4* x4 = reinterpret_cast<const float4*>(x);
             const int G4 = G >> 2;
             for (int base = 0; base < G4; base += 128) {
@@ -276,7 +294,7 @@ rank_warp_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
 // returns 0 on success; *may_overflow tells the caller to run the CTA kernel on flagged rows
 int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                      __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask) {
+                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr) {
     int cap = 64;
     while (cap < G && cap < RW_CAP) cap <<= 1;          // never more than the row can hold
     const int g_pad = (G + 7) & ~7;
@@ -296,7 +314,7 @@ int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, cons
     if (blocks > max_blocks) blocks = max_blocks;
     rank_warp_kernel<<<(unsigned)blocks, RW_WARPS * 32, smem, st>>>(X, ldx, row_index, col_index, M, G, cap, g_pad, d_hi,
                                                                   d_lo, ldd, inv_norm, flags, xnorm, rank2, drop_mode,
-                                                                  only_mask);
+                                                                  only_mask, csr);
     MN_LAUNCH_CHECK();
     return 0;
 }

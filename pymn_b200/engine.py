@@ -55,6 +55,32 @@ def _i32(a):
 
 
 @dataclass
+class CsrMatrix:
+    """Expression matrix in CSR form on the device (scipy.sparse.csr_matrix layout)."""
+    indptr: torch.Tensor       # int64 [n_rows + 1]
+    indices: torch.Tensor      # int32 [nnz]
+    data: torch.Tensor         # float32 [nnz]
+    shape: tuple
+
+
+def to_device_matrix(X):
+    """Dense array / tensor -> float32 CUDA tensor; scipy.sparse matrix -> CsrMatrix (no densification:
+    only the stored values cross PCIe)."""
+    from scipy import sparse
+    if isinstance(X, CsrMatrix):
+        return X
+    if sparse.issparse(X):
+        csr = X.tocsr()
+        if not csr.has_canonical_format:
+            csr = csr.copy()
+            csr.sum_duplicates()
+        return CsrMatrix(to_device(np.asarray(csr.indptr, dtype=np.int64)),
+                         to_device(np.asarray(csr.indices, dtype=np.int32)),
+                         to_device(np.asarray(csr.data, dtype=np.float32)), tuple(csr.shape))
+    return to_device(X, torch.float32)
+
+
+@dataclass
 class RankedCells:
     d_hi: torch.Tensor
     d_lo: torch.Tensor | None
@@ -69,9 +95,14 @@ class RankedCells:
 
 def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
                    want_xnorm=False, want_rank2=False) -> RankedCells:
-    """K1.  X: float32 CUDA [N, Gx] row-major."""
-    assert X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
-    dev = X.device
+    """K1.  X: float32 CUDA [N, Gx] row-major, or a CsrMatrix."""
+    is_csr = isinstance(X, CsrMatrix)
+    if is_csr:
+        assert col_index is None, "column sub-setting of a CSR matrix is not supported"
+        dev = X.data.device
+    else:
+        assert X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
+        dev = X.device
     M = int(row_index.numel()) if row_index is not None else int(X.shape[0])
     G = int(col_index.numel()) if col_index is not None else int(X.shape[1])
     ldd = (G + 63) // 64 * 64
@@ -81,7 +112,10 @@ def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
     flags = torch.empty((M,), dtype=torch.uint8, device=dev)
     xnorm = torch.empty((M, G), dtype=torch.float32, device=dev) if want_xnorm else None
     rank2 = torch.empty((M, G), dtype=torch.int32, device=dev) if want_rank2 else None
-    if M > 0:
+    if M > 0 and is_csr:
+        _lib.call("mn_rank_normalize_csr", X.indptr, X.indices, X.data, row_index, M, G, d_hi, d_lo, ldd,
+                  inv_norm, flags, xnorm, rank2, int(drop_mode))
+    elif M > 0:
         _lib.call("mn_rank_normalize", X, int(X.stride(0)), row_index, col_index, M, G, d_hi, d_lo, ldd,
                   inv_norm, flags, xnorm, rank2, int(drop_mode))
     return RankedCells(d_hi, d_lo, ldd, inv_norm, flags, M, G, xnorm, rank2)
@@ -173,7 +207,7 @@ def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
     """metaNeighborUS_fast.  X: numpy / torch float32 [N, G] (input cell order).
     Returns dict(table [L, L] rows = test labels, cols = train labels (both row order),
     auroc (one-vs-rest table), n_pos [L], flags uint8 [N] in device row order)."""
-    Xd = to_device(X, torch.float32)
+    Xd = to_device_matrix(X)
     rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
     L, S = len(lay.row_labels), len(lay.studies)
     C, n_valid = centroids(rc, _i32(lay.lab_row_off), L, extra_rows=S)
@@ -189,12 +223,12 @@ def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.
                   n_model_studies: int, ndn=True, ovb=False):
     """MetaNeighborUS_from_trained.  model_centroids float [L_train, G] (rows = model
     columns), model_n [L_train], model_study int [L_train]."""
-    Xd = to_device(X, torch.float32)
+    Xd = to_device_matrix(X)
     rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
     Lt = int(model_centroids.shape[0])
-    C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=Xd.device)
+    C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)
     C[:Lt, :rc.G] = to_device(np.asarray(model_centroids, np.float32))
-    n_valid = torch.zeros((Lt + n_model_studies,), dtype=torch.float32, device=Xd.device)
+    n_valid = torch.zeros((Lt + n_model_studies,), dtype=torch.float32, device=rc.d_hi.device)
     n_valid[:Lt] = to_device(np.asarray(model_n, np.float32))
     train_study = _i32(model_study)
     if ndn:
@@ -206,7 +240,7 @@ def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.
 
 def train_model(X, lay: LabelLayout):
     """trainModel: returns dict(centroids float32 [L, G], n_cells [L], flags [N] device row order)."""
-    Xd = to_device(X, torch.float32)
+    Xd = to_device_matrix(X)
     rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=1)
     L = len(lay.row_labels)
     C, n_valid = centroids(rc, _i32(lay.lab_row_off), L)
@@ -283,7 +317,7 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
     if t: t.start("rank_normalize")
     rc = rank_normalize(Xd, row_index=perm, drop_mode=0)
     if t: t.stop("rank_normalize")
-    dev = Xd.device
+    dev = rc.d_hi.device
     N = rc.M
     hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
     if t: t.start("corr_hist")
@@ -313,7 +347,7 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
 def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):
     """metaNeighborUS_default.  Returns dict(auroc [L, L] rows = TEST labels, cols = TRAIN
     labels, both in row order -- the caller transposes / reorders, MetaNeighborUS.py:213)."""
-    Xd = to_device(X, torch.float32)
+    Xd = to_device_matrix(X)
     L, S = len(lay.row_labels), len(lay.studies)
     auc, n_pos, flags, hist = us_default_device(Xd, _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off), L, S,
                                                 ndn, nbins)

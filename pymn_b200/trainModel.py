@@ -5,7 +5,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, to_dense_f32
+from .utils import label_layout, prepare_matrix
 
 
 def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
@@ -26,7 +26,7 @@ def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
     assert var_genes.shape[0] > 2, "Must have at least 2 genes"
 
     sub = adata[:, var_genes]
-    X = to_dense_f32(sub.X)
+    X = prepare_matrix(sub.X)
     S = np.asarray(sub.obs[study_col].values, dtype=object)
     C = np.asarray(sub.obs[ct_col].values, dtype=object)
     lay = label_layout(S, C)

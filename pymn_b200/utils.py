@@ -130,6 +130,15 @@ def joint_layout(study, ctype):
     return lay, ct_uniq
 
 
+def prepare_matrix(X):
+    """What the device pipelines ingest: a scipy CSR matrix as it is (AnnData's native layout; only
+    the stored values are uploaded), anything else as a dense C-contiguous float32 array."""
+    from scipy import sparse
+    if sparse.issparse(X):
+        return X.tocsr()
+    return np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+
+
 def to_dense_f32(X) -> np.ndarray:
     """Dense C-contiguous float32 cells x genes (the reference densifies at
     utils.py:136-139; CSR ingestion on device is SURVEY section 8f 'next')."""
