@@ -282,21 +282,26 @@ def run_ours(args):
         }
         dom = max(kern, key=lambda k: kern[k]["ms"])
         peak = peaks["tf_sust"]
+        # DRAM bytes per launch measured by `ncu --set full` on this very command (profiles/, N=1 only)
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_c2.json")
+        if world == 1 and args.config == "c2" and os.path.isfile(tpath):
+            traffic = json.load(open(tpath))
         roof = {}
         for k, v in kern.items():
             ach = v["flop"] / (v["ms"] / 1e3) / 1e12
             roof[k] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                       "traffic": None, "ms_per_launch": v["ms"],
+                       "traffic": traffic.get(k), "ms_per_launch": v["ms"],
                        "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['src']})"}
         hbm = {}
         bytes_rank = 6.0 * N * G           # K1: 4 B read + 2 B fp16 plane written per element
         ach = bytes_rank / (stage_ms["rank_normalize"] / 1e3) / 1e9
         hbm["rank_normalize"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                                 "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": stage_ms["rank_normalize"]}
+                                 "frac": ach / peaks["hbm"], "traffic": traffic.get("rank_normalize"), "ms_per_launch": stage_ms["rank_normalize"]}
         bytes_auroc = 4.0 * N * L + 4.0 * N
         ach = bytes_auroc / (stage_ms["auroc"] / 1e3) / 1e9
         hbm["auroc"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": stage_ms["auroc"]}
+                        "frac": ach / peaks["hbm"], "traffic": traffic.get("auroc"), "ms_per_launch": stage_ms["auroc"]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -11,12 +11,14 @@
 // (hi*hi + hi*lo + lo*hi) are extra accumulation passes into the same TMEM
 // accumulator -- the fp16 analogue of a 3xTF32 split, but with exact limbs.
 //
-// Kernel anatomy (persistent, one CTA per SM, 192 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) -> smem ring
+// Kernel anatomy (persistent, one CTA per SM, 320 threads):
+//   warp 0      TMA producer: claims tiles from a global atomic counter (dynamic scheduler), issues
+//               cp.async.bulk.tensor 2D tiles (128B swizzle) -> smem ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1,
 //               kind::f16, M=128, N=BN, K=16), tcgen05.commit -> mbarriers
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) from one of
-//               two TMEM accumulator stages while the next tile's MMAs run
+//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns per warp; two warps per TMEM lane
+//               quarter, each half of the columns) from one of two TMEM accumulator stages while
+//               the next tile's MMAs run
 // Epilogues:
 //   EPI_STORE  votes_fast: scale + addend, store column-major FP32   (MetaNeighborUS.py:361-366)
 //   EPI_HIST   pass 1 of the global rank: rho -> shared-memory histogram (utils.py:44-45)
