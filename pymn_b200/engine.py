@@ -182,25 +182,66 @@ def one_vs_best(votes, ncols, denom, col_denom, seg_lab_off, n_seg, lab_row_off,
 def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_train, train_study, n_train_studies,
                              ndn: bool, ovb: bool):
     """predict_and_score (MetaNeighborUS.py:310-387) for all test studies at once.
-    C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids."""
+    C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids.
+
+    Multi-GPU (torch.distributed initialised, one process per GPU): every train column is an independent
+    unit of the vote GEMM, the AUROC sort and the one-vs-best contest, so the columns are dealt round-robin
+    to the ranks (K1 and the centroid sums are replicated: a few ms) and the L_test x L_train table is
+    assembled with one all-gather of the column slices."""
     dev = rc.d_hi.device
-    n_b = n_train + (n_train_studies if ndn else 0)
-    b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
-    addend = n_valid[:n_b].contiguous() if ndn else None
-    out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
-    denom = out[n_train:] if ndn else None
-    col_denom = train_study if ndn else None
-    kept = rc.inv_norm > 0
-    cell_label = torch.where(kept, _i32(lay.cell_label), torch.full_like(_i32(lay.cell_label), -1))
+    rank, world, _ = dist_shard()
     n_lab = len(lay.row_labels)
     n_seg = len(lay.studies)
+    cols = torch.arange(rank, n_train, world, device=dev) if world > 1 else None
+    n_loc = int(cols.numel()) if cols is not None else n_train
+    kept = rc.inv_norm > 0
+    cell_label = torch.where(kept, _i32(lay.cell_label), torch.full_like(_i32(lay.cell_label), -1))
     seg_off = _i32(lay.seg_off)
-    auc, n_pos = auroc(out, n_train, denom, col_denom, seg_off, n_seg, cell_label, n_lab)
-    res = auc
-    if ovb:
-        res = one_vs_best(out, n_train, denom, col_denom, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
-                          cell_label, n_lab, auc)
-    return res, auc, n_pos
+    if cols is not None:
+        rows = torch.cat([cols, torch.arange(n_train, n_train + n_train_studies, device=dev)])
+        C = C.index_select(0, rows).contiguous()
+        n_valid = n_valid.index_select(0, rows).contiguous()
+        train_study = train_study.index_select(0, cols).contiguous()
+    if n_loc > 0:
+        n_b = n_loc + (n_train_studies if ndn else 0)
+        b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
+        addend = n_valid[:n_b].contiguous() if ndn else None
+        out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
+        denom = out[n_loc:] if ndn else None
+        col_denom = train_study if ndn else None
+        auc, n_pos = auroc(out, n_loc, denom, col_denom, seg_off, n_seg, cell_label, n_lab)
+        res = auc
+        if ovb:
+            res = one_vs_best(out, n_loc, denom, col_denom, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
+                              cell_label, n_lab, auc)
+    else:
+        auc = res = torch.empty((n_lab, 0), dtype=torch.float64, device=dev)
+        n_pos = torch.zeros((n_lab,), dtype=torch.int32, device=dev)
+    if cols is None:
+        return res, auc, n_pos
+    return (_gather_columns(res, n_train, rank, world), _gather_columns(auc, n_train, rank, world),
+            _allreduce_max(n_pos))
+
+
+def _gather_columns(local: torch.Tensor, n_total: int, rank: int, world: int) -> torch.Tensor:
+    """All-gather the per-rank column slices (column j lives on rank j % world) into [rows, n_total]."""
+    import torch.distributed as dist
+    n_max = (n_total + world - 1) // world
+    buf = torch.full((local.shape[0], n_max), float("nan"), dtype=local.dtype, device=local.device)
+    buf[:, :local.shape[1]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = torch.empty((local.shape[0], n_total), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        n_r = len(range(r, n_total, world))
+        out[:, r::world] = parts[r][:, :n_r]
+    return out
+
+
+def _allreduce_max(t: torch.Tensor) -> torch.Tensor:
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
 
 
 def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):

@@ -31,6 +31,18 @@ def main():
     single = engine.us_default_device(*args, shard=(0, 1, None))[0].cpu().numpy()
     assert np.array_equal(multi, single, equal_nan=True), "sharded full-network table differs from the single-GPU one"
 
+    # centroid (fast) path: train columns are dealt to the ranks, tables all-gathered
+    for ovb in (False, True):
+        sharded = engine.us_fast(x, lay, True, ovb)
+        saved_shard = engine.dist_shard
+        engine.dist_shard = lambda: (0, 1, None)
+        try:
+            alone = engine.us_fast(x, lay, True, ovb)
+        finally:
+            engine.dist_shard = saved_shard
+        assert np.array_equal(sharded["table"], alone["table"], equal_nan=True), f"fast path differs (ovb={ovb})"
+        assert np.array_equal(sharded["n_pos"], alone["n_pos"])
+
     genes = np.array([f"g{i}" for i in range(300)], dtype=object)
     inp = dict(X=x, study=s, ctype=c, genes=genes, hvg=np.ones(300, bool))
     gs = pd.DataFrame(make_genesets(5, 300, 5, 10, 120), index=genes, columns=[f"set{j}" for j in range(5)])
