@@ -80,7 +80,7 @@ def MetaNeighbor(
     assert study_col in adata.obs_keys(), "Study Col not in adata"
     assert ct_col in adata.obs_keys(), "Cluster Col not in adata"
     assert (
-        np.unique(adata.obs[study_col]).shape[0] > 1
+        pd.unique(adata.obs[study_col].values).shape[0] > 1
     ), f"Found only 1 unique study_id in {study_col}"
 
     shared_genes = np.intersect1d(adata.var_names.values, genesets.index.values)

@@ -127,7 +127,8 @@ def MetaNeighborUS(adata,
          run in fast version mode or use a pretrained model"
 
     if trained_model is None:
-        assert (np.unique(adata.obs[study_col].values).shape[0] > 1), "Need more than 1 study"
+        # (hash-based unique: np.unique would sort 10^5-10^6 label strings just to count them)
+        assert (pd.unique(adata.obs[study_col].values).shape[0] > 1), "Need more than 1 study"
         if fast_version:
             assert (adata.obs[study_col].dtype.name != "category"
                     ), "Study Col is a category type, cast to either string or int"
