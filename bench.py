@@ -281,6 +281,7 @@ def run_ours(args):
             "corr_vote": {"ms": stage_ms["corr_vote"], "flop": flops_vote},
         }
         dom = max(kern, key=lambda k: kern[k]["ms"])
+        sp = dict(engine.LAST_SPILL)
         peak = peaks["tf_sust"]
         # DRAM bytes per launch measured by `ncu --set full` on this very command (profiles/, N=1 only)
         traffic = {}
@@ -294,6 +295,15 @@ def run_ours(args):
                        "traffic": traffic.get(k), "ms_per_launch": v["ms"],
                        "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({peaks['src']})"}
         hbm = {}
+        if sp.get("spill_tiles", 0) >= sp.get("total_tiles", 1):
+            # pass 2 streamed every tile from the rho spill: an HBM-bound kernel, 4 B per cell pair of the
+            # upper triangle (tile granularity: spill_tiles x 128 x 256 x 4 B)
+            b = float(sp["spill_tiles"]) * sp["tile_bytes"]
+            ach = b / (stage_ms["corr_vote"] / 1e3) / 1e9
+            roof["corr_vote"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                                 "frac": ach / peaks["hbm"], "traffic": traffic.get("corr_vote_spill"),
+                                 "ms_per_launch": stage_ms["corr_vote"],
+                                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['src']})"}
         bytes_rank = 6.0 * N * G           # K1: 4 B read + 2 B fp16 plane written per element
         ach = bytes_rank / (stage_ms["rank_normalize"] / 1e3) / 1e9
         hbm["rank_normalize"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
@@ -308,6 +318,8 @@ def run_ours(args):
             "dtype": "f16 exact-integer operands, f32 TMEM accumulate, int64 vote sums",
             "data": "synthetic",
             "config": {"workload": desc, "n_cells": N, "n_genes": G, "n_labels": L, "nbins": engine.DEFAULT_NBINS,
+                       "rho_spill": {"tiles": sp.get("spill_tiles", 0), "of": sp.get("total_tiles", 0),
+                                     "gb": round(sp.get("spill_tiles", 0) * sp.get("tile_bytes", 0) / 1e9, 1)},
                        "l2": "inputs (1.6 GB fp32 + 0.8 GB fp16 planes) are larger than the 126 MB L2",
                        "parallelism": f"row-tile sharding x{world}" if world > 1 else "single GPU"},
             "clocks": clocks,

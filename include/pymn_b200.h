@@ -119,7 +119,7 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  * Pass 1: mn_corr_hist   -- rho tiles on tensor cores -> exact histogram of rho
  *                           over pairs i<j, i in [row0,row1), both cells kept
  * LUT   : mn_corr_lut    -- histogram -> fixed-point CDF table W = (rank-1)/max
- * Pass 2: mn_corr_vote   -- rho tiles again -> W via LUT -> integer vote sums
+ * Pass 2: mn_corr_vote   -- rho tiles again (or from the rho spill) -> W via LUT -> integer vote sums
  *   votes  uint64 [N, L]  sum_j W_fix(rho_ij) [label(j)==l]   (W_fix = W * 2^26; j != i)
  *   degree uint64 [N]     sum_j W_fix(rho_ij)                 (j != i)
  * Both accumulate with integer atomics (exact, order-independent, so the
@@ -133,14 +133,27 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  */
 int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
                  int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
-                 int32_t G, int32_t nbins, uint64_t* hist, mn_stream_t stream);
+                 int32_t G, int32_t nbins, uint64_t* hist, uint32_t* spill, int64_t spill_tiles,
+                 mn_stream_t stream);
+/* The rho spill (optional; spill = NULL, spill_tiles = 0 turns it off).  The 180 GB of HBM are large
+ * enough to keep what pass 1 computes: the first `spill_tiles` tiles (128 x 256 pairs each, in the
+ * kernel's own tile order) leave their bin positions -- 16.16 fixed point, 4 B per cell pair, 80 GB for
+ * 200,000 cells -- in `spill`, and pass 2 streams them back (an HBM-bound kernel) instead of
+ * recomputing those tiles on the tensor cores; tiles beyond `spill_tiles` are recomputed.  Both
+ * routes feed the same integers into the same weight map, so the vote sums are bit-identical for
+ * any `spill_tiles`.  mn_corr_spill_layout reports the tile count and size of one shard: a buffer of
+ * n_tiles * tile_bytes holds everything.  The same (N, row0, row1, shard, nbins) must be passed to
+ * the layout query, mn_corr_hist and mn_corr_vote. */
+int mn_corr_spill_layout(int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
+                         int32_t nbins, int64_t* n_tiles /* host */, int64_t* tile_bytes /* host */);
 /* n_diag = number of diagonal entries (all cells, they tie at rho = 1 -- utils.py:72) */
 int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut /* [nbins+1] */,
                 mn_stream_t stream);
 int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
                  int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
                  int32_t G, int32_t nbins, const uint32_t* lut, const int32_t* label, int32_t L,
-                 uint64_t* votes, uint64_t* degree, mn_stream_t stream);
+                 uint64_t* votes, uint64_t* degree, const uint32_t* spill, int64_t spill_tiles,
+                 mn_stream_t stream);
 
 /* votes uint64 [N, L] + degree uint64 [N] -> float32 column-major [L, ldo] vote matrix.
  * Adds the diagonal (W_ii = 1, utils.py:74) to votes[i, label[i]] and degree[i];

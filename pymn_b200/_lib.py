@@ -29,9 +29,10 @@ SIGNATURES = {
     "mn_group_sum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "mn_split_f16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "mn_votes_fast": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
-    "mn_corr_hist": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "mn_corr_hist": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "mn_corr_spill_layout": (C.c_int, [_i64, _i64, _i64, _i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
     "mn_corr_lut": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
-    "mn_corr_vote": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "mn_corr_vote": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "mn_votes_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "mn_loso_finalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
     "mn_auroc_workspace_bytes": (_i64, [_i32, _i64]),
@@ -89,6 +90,16 @@ def call(name, *args):
 
 def launch_count() -> int:
     return int(load().mn_launch_count())
+
+
+def corr_spill_layout(n: int, row0: int, row1: int, shard_rank: int, shard_world: int, nbins: int):
+    """(number of tiles, bytes per tile) of one shard's rho spill."""
+    lib = load()
+    nt, tb = _i64(0), _i64(0)
+    rc = lib.mn_corr_spill_layout(n, row0, row1, shard_rank, shard_world, nbins, C.byref(nt), C.byref(tb))
+    if rc != 0:
+        raise RuntimeError(f"mn_corr_spill_layout failed (rc={rc}): {lib.mn_last_error().decode()}")
+    return int(nt.value), int(tb.value)
 
 
 def auroc_workspace_bytes(ncols: int, m: int) -> int:

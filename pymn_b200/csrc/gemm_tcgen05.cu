@@ -72,6 +72,11 @@ struct GemmParams {
     int L;
     unsigned long long* votes;     // [M, L]
     unsigned long long* degree;    // [M]
+    // rho spill (EPI_HIST writes, vote_spill_kernel reads): tile t < spill_tiles of the linear tile
+    // order keeps its BM x BN fixed-point bin positions in HBM so that pass 2 need not recompute them
+    uint32_t* spill;
+    int spill_tiles;
+    int tile_base;           // first linear tile index of this launch (pass 2 over the tiles that were not spilled)
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -189,6 +194,144 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
 // position of rho on the bin axis; pass 1 and pass 2 must agree bit for bit
 __device__ __forceinline__ float rho_binpos(float acc, float inv_i_half, float inv_j, float half_bins) {
     return fmaf(acc * inv_i_half, inv_j, half_bins);      // (rho + 1) * nbins / 2
+}
+// ... as 16.16 fixed point: bin = q >> 16, position inside the bin = q & 0xffff.  NaN (a dropped
+// cell's scale) and negative values convert to 0.  This integer is what pass 1 bins, what the rho
+// spill stores and what pass 2 maps to a weight, so the three can never disagree.
+constexpr int Q_FRAC_BITS = 16;
+__device__ __forceinline__ uint32_t rho_q(float acc, float inv_i_half, float inv_j, float half_bins) {
+    return __float2uint_rd(rho_binpos(acc, inv_i_half, inv_j, half_bins) * (float)(1 << Q_FRAC_BITS));
+}
+// W (2^MN_W_SHIFT fixed point) by linear interpolation inside the bin; tab[top + 1] == tab[top]
+__device__ __forceinline__ uint32_t w_from_q(uint32_t q, const uint32_t* tab, unsigned top) {
+    const unsigned b = min(q >> Q_FRAC_BITS, top);
+    const uint32_t lo = tab[b], hi = tab[b + 1];
+    return lo + __umulhi(hi - lo, q << (32 - Q_FRAC_BITS));
+}
+
+
+// ------------------------------------------------------------------ pass-2 vote accumulation
+// One thread = one row (cell i) of a tile; it walks the tile's columns in chunks of 32 fixed-point bin
+// positions q_ij (from the tensor core or from the rho spill).
+//   row side:    votes[i, label(j)] += W_ij as a per-thread running sum over the label runs of the
+//                columns (cells are sorted by label, so a tile holds 1-3 runs), one 64-bit atomic per run;
+//   column side: votes[j, label(i)] += W_ij through a 32 x 32 shuffle transpose-reduce per warp (rows
+//                of a warp almost always share a label); per-warp column sums land in shared memory
+//                (colw) and are merged across the row-quarter warps by vote_merge_columns.
+struct VoteRows {
+    unsigned long long run_acc;
+    unsigned long long* vrow;
+    int cur_lab, lab_i;
+    unsigned gmask;
+    bool warp_uniform, grp_leader;
+
+    __device__ __forceinline__ void begin(int lab_i_, unsigned long long* vrow_, int lane) {
+        run_acc = 0ull;
+        cur_lab = 0;
+        lab_i = lab_i_;
+        vrow = vrow_;
+        gmask = __match_any_sync(0xffffffffu, lab_i);
+        warp_uniform = (gmask == 0xffffffffu);
+        grp_leader = (gmask & lanemask_lt()) == 0;
+    }
+    __device__ __forceinline__ void flush() {
+        if (run_acc) {
+            atomicAdd(vrow + cur_lab, run_acc);
+            run_acc = 0ull;
+        }
+    }
+    // r: 32 bin positions in, weights out.  brk: bit c set = a label run starts at column c of the chunk.
+    // vcol = &votes[(first column of the chunk) * L]
+    __device__ __forceinline__ void chunk(uint32_t (&r)[32], unsigned brk, const int32_t* s_lab_c0,
+                                          const uint32_t* s_table, unsigned top, bool sym,
+                                          unsigned long long* vcol, int L, uint64_t pol_ef, uint32_t* colw_c0,
+                                          int lane) {
+        uint32_t mycol = 0u;
+        if (brk & 1u) {                                  // warp-uniform: a label run starts with this chunk
+            flush();
+            cur_lab = s_lab_c0[0];
+        }
+        if ((brk >> 1) == 0u) {
+            // fast path (almost every chunk): one label run -> branch-free
+            uint32_t acc32 = 0u;                         // 32 weights <= 2^26 each fit 32 bits
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const uint32_t w = w_from_q(r[c], s_table, top);
+                acc32 += w;
+                r[c] = w;
+            }
+            run_acc += acc32;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                if (c > 0 && (brk & (1u << c))) {
+                    flush();
+                    cur_lab = s_lab_c0[c];
+                }
+                const uint32_t w = w_from_q(r[c], s_table, top);
+                run_acc += w;
+                r[c] = w;
+            }
+        }
+        if (sym) {
+            if (warp_uniform) {
+                // 32 x 32 transpose-reduce: 31 shuffles leave in lane l the sum over the warp's
+                // 32 rows of column l of the chunk  (<= 32 * 2^26, fits 32 bits)
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int c = 0; c < off; ++c) {
+                        const uint32_t send = up ? r[c] : r[c + off];
+                        const uint32_t keep = up ? r[c + off] : r[c];
+                        r[c] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                mycol = r[0];
+            } else {                                     // rows of several labels in one warp (rare)
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const uint32_t s = __reduce_add_sync(gmask, r[c]);
+                    if (grp_leader && s) red_add_u64_hint(vcol + (int64_t)c * L + lab_i, (unsigned long long)s, pol_ef);
+                }
+            }
+            colw_c0[lane] = mycol;
+        }
+    }
+    __device__ __forceinline__ void finish() { flush(); }
+};
+
+// Column side of one tile: s_colw [EPI_WARPS][BN/2] per-warp column sums (warps 0-3 = first half of the
+// columns, 4-7 = second half; s_wlab[w] = the row label of warp w, or -2 if its rows were mixed and
+// already flushed).  Call after a barrier over the 8 warps.
+template <int BN>
+__device__ __forceinline__ void vote_merge_columns(const uint32_t* s_colw, const int32_t* s_wlab,
+                                                   unsigned long long* votes, int64_t n0, int L, uint64_t pol_ef,
+                                                   int ew, int lane, bool skip) {
+    constexpr int HALF_COLS = BN / 2;
+    const int et = ew * 32 + lane;
+    const int lab0 = s_wlab[0];
+    bool tile_uniform = lab0 >= 0;
+#pragma unroll
+    for (int w8 = 1; w8 < EPI_WARPS; ++w8) tile_uniform = tile_uniform && (s_wlab[w8] == lab0);
+    if (tile_uniform) {
+        for (int c = et; c < BN; c += EPI_THREADS) {
+            const uint32_t* src = s_colw + (c / HALF_COLS) * 4 * HALF_COLS + (c % HALF_COLS);
+            const unsigned long long sum = (unsigned long long)src[0] + src[HALF_COLS] +
+                                           src[2 * HALF_COLS] + src[3 * HALF_COLS];
+            if (sum && !skip) red_add_u64_hint(votes + (n0 + c) * (int64_t)L + lab0, sum, pol_ef);
+        }
+    } else {
+        const int my_lab = s_wlab[ew];
+        if (my_lab >= 0) {
+            const uint32_t* src = s_colw + ew * HALF_COLS;
+            const int cbeg = (ew >> 2) * HALF_COLS;
+            for (int k = lane; k < HALF_COLS; k += 32) {
+                const uint32_t v = src[k];
+                if (v) red_add_u64_hint(votes + (n0 + cbeg + k) * (int64_t)L + my_lab, (unsigned long long)v, pol_ef);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ tile schedule
@@ -346,7 +489,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             uint32_t ph = 0, qph = 0;
             for (;;) {
                 mbar_wait(&qempty_bar[qs], qph ^ 1u);
-                const unsigned int t = atomicAdd(p.tile_counter, 1u);
+                const unsigned int t = atomicAdd(p.tile_counter, 1u) + (unsigned int)p.tile_base;
                 const int tile = (t < (unsigned int)p.total_tiles) ? (int)t : -1;
                 s_tileq[qs] = tile;
                 mbar_arrive(&qfull_bar[qs]);
@@ -495,6 +638,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const float inv_i_half = inv_i * half_bins;
                 const unsigned top = (unsigned)p.nbins, sink = (unsigned)p.nbins + 1u;
                 const bool row_live = inv_i > 0.f;
+                // rho spill: this warp's 32 x 32 chunks in tile-native order, [ew][chunk][k][lane] x 16 B
+                // (coalesced 512-byte stores); masked entries are stored as 0, which maps to W = lut[0] = 0
+                const bool do_spill = p.spill != nullptr && tile < p.spill_tiles;
+                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)tile * (size_t)(BM * BN)) +
+                            (size_t)(ew * (HALF_COLS / 32)) * 256 + lane;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
@@ -504,122 +652,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float inv_j = s_invb[c0 + c];
-                                const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
-                                unsigned b = min(__float2uint_rd(pos), top);
-                                b = (inv_j > 0.f) ? b : sink;
-                                atomicAdd(&s_table[b], 1u);
+                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                                const bool use = inv_j > 0.f;
+                                atomicAdd(&s_table[use ? min(qv >> Q_FRAC_BITS, top) : sink], 1u);
+                                r[c] = use ? qv : 0u;
                             }
                         } else {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float inv_j = s_invb[c0 + c];
-                                const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
-                                unsigned b = min(__float2uint_rd(pos), top);
-                                b = (inv_j > 0.f && (n0 + c0 + c > m)) ? b : sink;
-                                atomicAdd(&s_table[b], 1u);
+                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                                const bool use = inv_j > 0.f && (n0 + c0 + c > m);
+                                atomicAdd(&s_table[use ? min(qv >> Q_FRAC_BITS, top) : sink], 1u);
+                                r[c] = use ? qv : 0u;
                             }
                         }
+                    } else if (do_spill) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) r[c] = 0u;
+                    }
+                    if (do_spill) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            __stcs(sp + k * 32, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+                        sp += 256;
                     }
                 }
             } else {   // EPI_VOTE
                 // Every weight W_ij (j > i in `tri` mode: the network is symmetric, only the upper
-                // triangle is computed) is added to votes[i, label(j)] (row side: per-thread running
-                // sum over the label runs of the tile's columns) and, in `tri` mode, to
-                // votes[j, label(i)] (column side: one REDUX.SUM over the warp's 32 rows per column).
-                // Dropped cells carry NaN scales here: NaN propagates through the bin position, the
-                // float->uint conversions turn it into bin 0 / increment 0, and lut[0] == 0, so their
-                // weights vanish without a single predicate in the inner loop.
+                // triangle is computed) is added to votes[i, label(j)] (row side) and, in `tri` mode, to
+                // votes[j, label(i)] (column side); see VoteRows.  Dropped cells carry NaN scales here:
+                // NaN propagates through the bin position, the float->uint conversion turns it into
+                // q = 0 and lut[0] == 0, so their weights vanish without a predicate in the inner loop.
                 const float qnan = __int_as_float(0x7fc00000);
                 const float inv_i_half = (inv_i > 0.f) ? inv_i * half_bins : qnan;
-                const unsigned top = (unsigned)p.nbins;
                 const bool sym = p.tri != 0;
-                const int lab_i = p.label[row_ok ? m : p.M - 1];     // rows past the end carry zero weights
-                const unsigned gmask = __match_any_sync(0xffffffffu, lab_i);
-                const bool warp_uniform = (gmask == 0xffffffffu);
-                const bool grp_leader = (gmask & lanemask_lt()) == 0;
-                unsigned long long run_acc = 0ull;
-                int cur_lab = 0;
-                unsigned long long* vrow = p.votes + (row_ok ? m : 0) * (int64_t)p.L;
+                VoteRows vr;
+                vr.begin(p.label[row_ok ? m : p.M - 1], p.votes + (row_ok ? m : 0) * (int64_t)p.L, lane);
                 uint32_t* colw = s_colw + ew * HALF_COLS;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
-                    const unsigned brk = s_flush[c0 >> 5];
-                    uint32_t mycol = 0u;
-                    if (brk & 1u) {                              // warp-uniform: a label run starts with this chunk
-                        if (run_acc) {
-                            atomicAdd(vrow + cur_lab, run_acc);
-                            run_acc = 0ull;
-                        }
-                        cur_lab = s_lab[c0];
-                    }
-                    if ((brk >> 1) == 0u && !diag_tile) {
-                        // fast path (almost every chunk): one label run, no diagonal -> branch-free
-                        uint32_t acc32 = 0u;                     // 32 weights <= 2^26 each fit 32 bits
+                    if (!diag_tile) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
-                            const unsigned b = min(__float2uint_rd(pos), top);
-                            const float frac = pos - (float)b;
-                            const uint32_t lo = s_table[b], hi = s_table[b + 1];
-                            const uint32_t w = lo + __float2uint_rd(frac * (float)(hi - lo));
-                            acc32 += w;
-                            r[c] = w;
-                        }
-                        run_acc += acc32;
+                        for (int c = 0; c < 32; ++c)
+                            r[c] = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            if (c > 0 && (brk & (1u << c))) {
-                                if (run_acc) {
-                                    atomicAdd(vrow + cur_lab, run_acc);
-                                    run_acc = 0ull;
-                                }
-                                cur_lab = s_lab[c0 + c];
-                            }
-                            const float pos = rho_binpos(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
-                            const unsigned b = min(__float2uint_rd(pos), top);
-                            const float frac = pos - (float)b;
-                            const uint32_t lo = s_table[b], hi = s_table[b + 1];
-                            uint32_t w = lo + __float2uint_rd(frac * (float)(hi - lo));
-                            if (diag_tile) {
-                                const bool use = sym ? (n0 + c0 + c > m) : (n0 + c0 + c != m);
-                                w = use ? w : 0u;
-                            }
-                            run_acc += w;
-                            r[c] = w;
+                            const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
+                            const bool use = sym ? (n0 + c0 + c > m) : (n0 + c0 + c != m);
+                            r[c] = use ? qv : 0u;
                         }
                     }
-                    if (sym && !warp_uniform) {                  // rows of several labels in one warp (rare)
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const uint32_t s = __reduce_add_sync(gmask, r[c]);
-                            if (grp_leader && s)
-                                red_add_u64_hint(p.votes + (n0 + c0 + c) * (int64_t)p.L + lab_i, (unsigned long long)s, pol_ef);
-                        }
-                    }
-                    if (sym) {
-                        if (warp_uniform) {
-                            // 32 x 32 transpose-reduce: 31 shuffles leave in lane l the sum over the warp's
-                            // 32 rows of column c0 + l  (<= 32 * 2^26, fits 32 bits)
-#pragma unroll
-                            for (int off = 16; off >= 1; off >>= 1) {
-                                const bool up = (lane & off) != 0;
-#pragma unroll
-                                for (int c = 0; c < off; ++c) {
-                                    const uint32_t send = up ? r[c] : r[c + off];
-                                    const uint32_t keep = up ? r[c + off] : r[c];
-                                    r[c] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                                }
-                            }
-                            mycol = r[0];
-                        }
-                        colw[c0 - cbeg + lane] = mycol;
-                    }
+                    vr.chunk(r, s_flush[c0 >> 5], s_lab + c0, s_table, (unsigned)p.nbins, sym,
+                             p.votes + (n0 + c0) * (int64_t)p.L, p.L, pol_ef, colw + (c0 - cbeg), lane);
                 }
-                if (run_acc) atomicAdd(vrow + cur_lab, run_acc);
-                if (sym && lane == 0) s_wlab[ew] = warp_uniform ? lab_i : -2;
+                vr.finish();
+                if (sym && lane == 0) s_wlab[ew] = vr.warp_uniform ? vr.lab_i : -2;
             }
 
             // the accumulator stage is drained: hand it back to the MMA issuer
@@ -632,29 +723,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             }
 
             if (EPI == EPI_VOTE && p.tri != 0) {
-                // column side: merge the four row-quarter warps of each column half
                 epi_bar_sync();
-                const int lab0 = s_wlab[0];
-                bool tile_uniform = lab0 >= 0;
-#pragma unroll
-                for (int w8 = 1; w8 < EPI_WARPS; ++w8) tile_uniform = tile_uniform && (s_wlab[w8] == lab0);
-                if (tile_uniform) {
-                    for (int c = et; c < BN; c += EPI_THREADS) {
-                        const uint32_t* src = s_colw + (c / HALF_COLS) * 4 * HALF_COLS + (c % HALF_COLS);
-                        const unsigned long long sum = (unsigned long long)src[0] + src[HALF_COLS] +
-                                                       src[2 * HALF_COLS] + src[3 * HALF_COLS];
-                        if (sum && !p.dbg_skip_col) red_add_u64_hint(p.votes + (n0 + c) * (int64_t)p.L + lab0, sum, pol_ef);
-                    }
-                } else {
-                    const int my_lab = s_wlab[ew];
-                    if (my_lab >= 0) {
-                        const uint32_t* src = s_colw + ew * HALF_COLS;
-                        for (int k = lane; k < HALF_COLS; k += 32) {
-                            const uint32_t v = src[k];
-                            if (v) red_add_u64_hint(p.votes + (n0 + cbeg + k) * (int64_t)p.L + my_lab, (unsigned long long)v, pol_ef);
-                        }
-                    }
-                }
+                vote_merge_columns<BN>(s_colw, s_wlab, p.votes, n0, p.L, pol_ef, ew, lane, p.dbg_skip_col != 0);
             }
         }
         if (EPI == EPI_HIST) {
@@ -671,6 +741,102 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ pass 2 from the rho spill
+// Streams the bin positions pass 1 left in HBM (tile-native layout, see EPI_HIST) instead of
+// recomputing the tiles on the tensor cores: an HBM-bound kernel, 4 B per cell pair.  One CTA of
+// 8 warps plays the 8 epilogue warps of the GEMM kernel on one tile at a time (same thread <-> (row,
+// column) mapping, same VoteRows arithmetic, hence bit-identical vote sums); CTAs take blocks of
+// `tb` consecutive tiles round-robin, and every warp keeps its next 4 KB chunk in flight in
+// registers while it works on the current one.
+template <int BN>
+__global__ void __launch_bounds__(EPI_THREADS, 2) vote_spill_kernel(const GemmParams p, int tb) {
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    constexpr int HALF_COLS = BN / 2;
+    constexpr int NCH = HALF_COLS / 32;
+    uint32_t* s_table = s_dyn;                                             // [nbins + 2]
+    const int table_words = (p.nbins + 2 + 3) & ~3;
+    int32_t* s_lab = reinterpret_cast<int32_t*>(s_table + table_words);    // [BN]
+    uint32_t* s_flush = reinterpret_cast<uint32_t*>(s_lab + BN);           // [BN / 32]
+    uint32_t* s_colw = s_flush + BN / 32;                                  // [EPI_WARPS][BN / 2]
+    int32_t* s_wlab = reinterpret_cast<int32_t*>(s_colw + EPI_WARPS * HALF_COLS);   // [EPI_WARPS]
+
+    for (int i = threadIdx.x; i < p.nbins + 2; i += EPI_THREADS) s_table[i] = p.lut[i < p.nbins ? i : p.nbins];
+
+    const int ew = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int et = threadIdx.x;
+    const int row_in_tile = ((ew + 2) & 3) * 32 + lane;      // the GEMM's epilogue warp ew is CTA warp ew + 2
+    const int cbeg = (ew >> 2) * HALF_COLS;
+    const uint64_t pol_ef = l2_evict_first_policy();
+    const int n_blocks = (p.spill_tiles + tb - 1) / tb;
+    const uint4* base = reinterpret_cast<const uint4*>(p.spill) + (size_t)(ew * NCH) * 256 + lane;
+    constexpr size_t TILE_V4 = (size_t)BM * BN / 4;
+
+    TileIter it;
+    it.init(p, BN, 0);
+    int cur_tile = 0;
+    uint4 nx[8];
+    int blk = blockIdx.x;
+    if (blk < n_blocks) {
+        const uint4* src = base + (size_t)(blk * tb) * TILE_V4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nx[k] = __ldcs(src + k * 32);
+    }
+    for (; blk < n_blocks; blk += gridDim.x) {
+        const int t_end = min(p.spill_tiles, (blk + 1) * tb);
+        for (int tile = blk * tb; tile < t_end; ++tile) {
+            it.advance(tile - cur_tile);
+            cur_tile = tile;
+            const int64_t m0 = (int64_t)it.mt * BM, n0 = (int64_t)it.nt() * BN;
+            const int64_t m = m0 + row_in_tile;
+            for (int c = et; c < BN; c += EPI_THREADS) {
+                const int64_t n = n0 + c;
+                const bool ok = n < p.N;
+                const int lab = ok ? p.label[n] : 0;
+                s_lab[c] = lab;
+                const bool brk = (c == 0) || (c == HALF_COLS) || !ok || (n >= 1 && p.label[n - 1] != lab);
+                const unsigned msk = __ballot_sync(0xffffffffu, brk);
+                if (lane == 0) s_flush[c >> 5] = msk;
+            }
+            __syncthreads();          // metadata staged; the previous tile's column merge has been read
+            const bool row_ok = m < p.M;
+            VoteRows vr;
+            vr.begin(p.label[row_ok ? m : p.M - 1], p.votes + (row_ok ? m : 0) * (int64_t)p.L, lane);
+            uint32_t* colw = s_colw + ew * HALF_COLS;
+#pragma unroll
+            for (int ci = 0; ci < NCH; ++ci) {
+                uint32_t r[32];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    r[4 * k] = nx[k].x;
+                    r[4 * k + 1] = nx[k].y;
+                    r[4 * k + 2] = nx[k].z;
+                    r[4 * k + 3] = nx[k].w;
+                }
+                // next chunk of this warp: same tile, next tile of the block, or the first tile of the
+                // CTA's next block
+                int nt_tile = tile, nci = ci + 1;
+                if (nci == NCH) {
+                    nci = 0;
+                    nt_tile = tile + 1;
+                    if (nt_tile == t_end) nt_tile = (blk + (int)gridDim.x < n_blocks) ? (blk + (int)gridDim.x) * tb : -1;
+                }
+                if (nt_tile >= 0) {
+                    const uint4* src = base + (size_t)nt_tile * TILE_V4 + (size_t)nci * 256;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) nx[k] = __ldcs(src + k * 32);
+                }
+                const int c0 = cbeg + ci * 32;
+                vr.chunk(r, s_flush[c0 >> 5], s_lab + c0, s_table, (unsigned)p.nbins, true,
+                         p.votes + (n0 + c0) * (int64_t)p.L, p.L, pol_ef, colw + ci * 32, lane);
+            }
+            vr.finish();
+            if (lane == 0) s_wlab[ew] = vr.warp_uniform ? vr.lab_i : -2;
+            __syncthreads();
+            vote_merge_columns<BN>(s_colw, s_wlab, p.votes, n0, p.L, pol_ef, ew, lane, false);
+        }
     }
 }
 
@@ -792,6 +958,51 @@ static int sm_count() {
     return n;
 }
 
+// row tiles per L2 band of the tile schedule: 64 x 128 rows x (G * 2 B) of A = 32 MB at G = 2000, L2-resident
+static int gemm_band() {
+    if (const char* e = getenv("MN_GEMM_BAND")) {      // tuning knob
+        const int v = atoi(e);
+        if (v > 0) return v;
+    }
+    return 64;
+}
+
+// number of tiles of the triangular passes for one shard (the linear tile order of TileIter)
+static int64_t corr_tile_count(int64_t N, int64_t row0, int64_t row1, int shard_rank, int shard_world, int bn) {
+    const int n_tiles = (int)((N + bn - 1) / bn);
+    const int mt1 = (int)((row1 + BM - 1) / BM);
+    int64_t tiles = 0;
+    for (int mt = (int)(row0 / BM) + shard_rank; mt < mt1; mt += shard_world) {
+        const int first = (mt * BM) / bn;
+        if (first < n_tiles) tiles += n_tiles - first;
+    }
+    return tiles;
+}
+
+template <int BN>
+static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)((p.nbins + 2 + 3) & ~3) * 4 + (size_t)BN * 4 + (BN / 32) * 4 +
+                        (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4;
+    auto kern = vote_spill_kernel<BN>;
+    MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int tb = 8;
+    if (const char* e = getenv("MN_SPILL_TB")) {       // tuning knob
+        const int v = atoi(e);
+        if (v > 0) tb = v;
+    }
+    int per_sm = 2;
+    if (const char* e = getenv("MN_SPILL_CTAS")) {
+        const int v = atoi(e);
+        if (v > 0) per_sm = v;
+    }
+    const int n_blocks = (p.spill_tiles + tb - 1) / tb;
+    int grid = sm_count() * per_sm;
+    if (n_blocks < grid) grid = n_blocks;
+    kern<<<grid, EPI_THREADS, smem, st>>>(p, tb);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int BN, int EPI, int NCHAIN>
 static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, const __half* b_hi,
                        const __half* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
@@ -806,11 +1017,7 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     p.N = N;
     p.k_blocks = (G + BK - 1) / BK;
     p.n_tiles = (int)((N + BN - 1) / BN);
-    if (p.band <= 0) p.band = 64;      // 64 x 128 rows x (G * 2 B) of A per band: 32 MB at G = 2000, L2-resident
-    if (const char* e = getenv("MN_GEMM_BAND")) {      // tuning knob
-        const int v = atoi(e);
-        if (v > 0) p.band = v;
-    }
+    if (p.band <= 0) p.band = gemm_band();
     const size_t stage_bytes = (size_t)(BM + BN) * BK * 2;
     const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 2 + 3) & ~3) * 4;
     const size_t fixed = table + (size_t)BN * 12 + (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4 +
@@ -833,9 +1040,9 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     // number of tiles
     long long tiles = 0;
     for (int mt = p.mt0; mt < p.mt1; mt += p.mt_step) tiles += p.n_tiles - (p.tri ? (mt * BM) / BN : 0);
-    if (tiles <= 0) return 0;
+    if (tiles <= p.tile_base) return 0;
     int grid = sm_count();
-    if (tiles < grid) grid = (int)tiles;
+    if (tiles - p.tile_base < grid) grid = (int)(tiles - p.tile_base);
     // dynamic scheduler: one counter per launch out of a small rotating pool (launches on different
     // streams may overlap), zeroed on the launch stream
     static unsigned int* counters = nullptr;
@@ -906,7 +1113,7 @@ static int corr_terms(mn::GemmParams& p, bool has_lo) {
 
 int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t N,
                  int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world, int32_t G, int32_t nbins,
-                 uint64_t* hist, mn_stream_t stream) {
+                 uint64_t* hist, uint32_t* spill, int64_t spill_tiles, mn_stream_t stream) {
     using namespace mn;
     if (check_planes("mn_corr_hist", d_hi, ldd, G)) return 1;
     MN_CHECK_ARG(inv_norm && hist && N >= 1 && row0 >= 0 && row1 <= N && row0 < row1, "mn_corr_hist: bad arguments");
@@ -924,6 +1131,10 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.inv_b = inv_norm;
     p.nbins = nbins;
     p.hist = reinterpret_cast<unsigned long long*>(hist);
+    MN_CHECK_ARG(spill_tiles >= 0 && (spill_tiles == 0 || spill != nullptr), "mn_corr_hist: spill_tiles without a spill buffer");
+    MN_CHECK_ARG((reinterpret_cast<uintptr_t>(spill) & 15) == 0, "mn_corr_hist: spill must be 16-byte aligned");
+    p.spill = spill_tiles > 0 ? spill : nullptr;
+    p.spill_tiles = (int)(spill_tiles > INT_MAX ? INT_MAX : spill_tiles);
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
     // rows beyond row1 inside the last tile belong to the next shard: mask them via M
@@ -932,6 +1143,18 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     if (nbins <= 16384 && !getenv("MN_GEMM_BN128"))
         return launch_gemm<256, EPI_HIST, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     return launch_gemm<128, EPI_HIST, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+}
+
+int mn_corr_spill_layout(int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
+                         int32_t nbins, int64_t* n_tiles, int64_t* tile_bytes) {
+    using namespace mn;
+    MN_CHECK_ARG(n_tiles && tile_bytes && N >= 1 && row0 >= 0 && row1 <= N && row0 < row1 && (row0 % BM) == 0 &&
+                     shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world,
+                 "mn_corr_spill_layout: bad arguments");
+    const int bn = (nbins <= 16384 && !getenv("MN_GEMM_BN128")) ? 256 : 128;
+    *n_tiles = corr_tile_count(N, row0, row1, shard_rank, shard_world, bn);
+    *tile_bytes = (int64_t)BM * bn * 4;
+    return 0;
 }
 
 int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut, mn_stream_t stream) {
@@ -945,7 +1168,7 @@ int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* l
 int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t N,
                  int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world, int32_t G, int32_t nbins,
                  const uint32_t* lut, const int32_t* label, int32_t L, uint64_t* votes, uint64_t* degree,
-                 mn_stream_t stream) {
+                 const uint32_t* spill, int64_t spill_tiles, mn_stream_t stream) {
     using namespace mn;
     if (check_planes("mn_corr_vote", d_hi, ldd, G)) return 1;
     MN_CHECK_ARG(inv_norm && lut && label && votes && degree && N >= 1 && L >= 1 && row0 >= 0 && row1 <= N && row0 < row1,
@@ -973,8 +1196,25 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.degree = reinterpret_cast<unsigned long long*>(degree);
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
-    int rc;
-    if (nbins <= 16384 && !getenv("MN_GEMM_BN128"))
+    MN_CHECK_ARG(spill_tiles >= 0 && (spill_tiles == 0 || spill != nullptr), "mn_corr_vote: spill_tiles without a spill buffer");
+    const bool wide = nbins <= 16384 && !getenv("MN_GEMM_BN128");
+    int rc = 0;
+    // tiles [0, n_sp) of the linear tile order were spilled by pass 1: stream them from HBM;
+    // the tensor cores recompute only the rest
+    const int64_t total = corr_tile_count(N, row0, row1, shard_rank, shard_world, wide ? 256 : 128);
+    int64_t n_sp = (p.tri && spill) ? (spill_tiles < total ? spill_tiles : total) : 0;
+    if (n_sp > 0) {
+        p.spill = const_cast<uint32_t*>(spill);
+        p.spill_tiles = (int)n_sp;
+        p.M = row1;
+        p.N = N;
+        p.n_tiles = (int)((N + (wide ? 256 : 128) - 1) / (wide ? 256 : 128));
+        p.band = gemm_band();
+        rc = wide ? launch_vote_spill<256>(p, (cudaStream_t)stream) : launch_vote_spill<128>(p, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    p.tile_base = (int)n_sp;
+    if (wide)
         rc = launch_gemm<256, EPI_VOTE, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     else
         rc = launch_gemm<128, EPI_VOTE, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);

@@ -288,18 +288,66 @@ def train_model(X, lay: LabelLayout):
     return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=rc.flags.cpu().numpy())
 
 
+LAST_SPILL = {}         # what the last rho_spill_buffer call decided (bench.py reports it)
+_SPILL_CACHE = {}       # device index -> uint8 tensor reused between calls (allocating 80 GB is not free)
+
+
+def rho_spill_buffer(N: int, rank: int, world: int, nbins: int, dev, reserve_bytes: int = 0, max_tiles=None):
+    """Buffer for the rho spill of one shard (include/pymn_b200.h, mn_corr_spill_layout).
+
+    Pass 1 can leave the bin position of every cell pair in HBM (4 B per pair) so that pass 2 streams
+    them back instead of recomputing the tiles on the tensor cores.  Returns (buffer or None,
+    spill_tiles): as many tiles as fit into the free device memory minus ``reserve_bytes`` and a
+    safety margin; the rest is recomputed.  ``MN_SPILL_GB`` caps the buffer (0 disables the spill)."""
+    n_tiles, tile_bytes = _lib.corr_spill_layout(N, 0, N, rank, world, nbins)
+    if max_tiles is not None:
+        n_tiles = min(n_tiles, int(max_tiles))
+    cap = _os.environ.get("MN_SPILL_GB")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    cached = _SPILL_CACHE.get(idx)
+    have = int(cached.numel()) if cached is not None else 0
+    free, _total = torch.cuda.mem_get_info(idx)
+    # memory torch has cached but not handed out is reusable too
+    free += torch.cuda.memory_reserved(idx) - torch.cuda.memory_allocated(idx)
+    budget = free + have - int(reserve_bytes) - (4 << 30)
+    if cap is not None:
+        budget = min(budget, int(float(cap) * (1 << 30)))
+    want_tiles = max(0, min(n_tiles, budget // tile_bytes))
+    LAST_SPILL.update(total_tiles=_lib.corr_spill_layout(N, 0, N, rank, world, nbins)[0], tile_bytes=tile_bytes,
+                      spill_tiles=int(want_tiles) if want_tiles >= (8 if max_tiles is None else 1) else 0)
+    if want_tiles < (8 if max_tiles is None else 1):     # too small to pay for a second kernel
+        return None, 0
+    need = want_tiles * tile_bytes
+    if have < need:
+        _SPILL_CACHE.pop(idx, None)
+        del cached
+        torch.cuda.empty_cache()
+        cached = torch.empty((need,), dtype=torch.uint8, device=dev)
+        _SPILL_CACHE[idx] = cached
+    return cached, want_tiles
+
+
+def release_spill_cache():
+    _SPILL_CACHE.clear()
+    torch.cuda.empty_cache()
+
+
 def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAULT_NBINS, shard=(0, 1),
-                       reduce_fn=None):
+                       reduce_fn=None, spill_tiles=None):
     """K4/K5: two tensor-core passes over the (never stored) cell x cell network.
     ``shard`` = (rank, world): this GPU handles every world-th 128-row tile; ``reduce_fn``
     (an in-place sum all-reduce over ranks) is applied to the histogram before the LUT and
     to votes / degree afterwards -- integer sums, so the result is bit-identical for any
-    world size.  Returns (votes uint64-as-int64 [N, L], degree [N], hist [nbins], lut)."""
+    world size.  ``spill_tiles``: None = spill as many tiles as fit (rho_spill_buffer), an int caps the
+    number of spilled tiles (0 = recompute everything; the result does not depend on it).
+    Returns (votes uint64-as-int64 [N, L], degree [N], hist [nbins], lut)."""
     dev = rc.d_hi.device
     N = rc.M
     rank, world = shard
     hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
-    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist)
+    spill, n_sp = rho_spill_buffer(N, rank, world, nbins, dev, reserve_bytes=N * (L + 1) * 8, max_tiles=spill_tiles)
+    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist,
+              spill, n_sp)
     if reduce_fn is not None:
         reduce_fn(hist)
     lut = torch.empty((nbins + 1,), dtype=torch.int32, device=dev)
@@ -307,7 +355,7 @@ def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAU
     votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
     degree = torch.zeros((N,), dtype=torch.int64, device=dev)
     _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, lut,
-              label, L, votes, degree)
+              label, L, votes, degree, spill, n_sp)
     if reduce_fn is not None:
         reduce_fn(votes)
         reduce_fn(degree)
@@ -350,7 +398,8 @@ class StageTimer:
         return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in self.events.items()}
 
 
-def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAULT_NBINS, shard=None, timer=None):
+def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAULT_NBINS, shard=None, timer=None,
+                      spill_tiles=None):
     """Device-resident full-network pipeline: every argument already lives in HBM.
     Returns (auroc float64 [L, L] rows = test labels, n_pos, flags, hist)."""
     rank, world, reduce_fn = shard if shard is not None else dist_shard()
@@ -361,8 +410,11 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
     dev = rc.d_hi.device
     N = rc.M
     hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
+    spill, n_sp = rho_spill_buffer(N, rank, world, nbins, dev, reserve_bytes=N * (L + 1) * 8 + N * L * 4 + (1 << 30),
+                                   max_tiles=spill_tiles)
     if t: t.start("corr_hist")
-    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist)
+    _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist,
+              spill, n_sp)
     if t: t.stop("corr_hist")
     if reduce_fn is not None:
         reduce_fn(hist)
@@ -372,7 +424,7 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
     degree = torch.zeros((N,), dtype=torch.int64, device=dev)
     if t: t.start("corr_vote")
     _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, lut,
-              cell_label, L, votes, degree)
+              cell_label, L, votes, degree, spill, n_sp)
     if t: t.stop("corr_vote")
     if reduce_fn is not None:
         reduce_fn(votes)

@@ -250,8 +250,11 @@ def test_corr_hist_and_votes(eng, n, g):
         assert np.array_equal(got_hist, ref_hist), "all partial sums are exact integers < 2^24: histogram must be exact"
     lut_h = lut.cpu().numpy().astype(np.int64)
     assert np.all(np.diff(lut_h) >= 0) and lut_h[0] == 0 and lut_h[-1] <= (1 << 26)
-    frac = np.clip(binpos - b, 0, 1).astype(np.float32)
-    w = lut_h[b] + np.floor(frac * (lut_h[b + 1] - lut_h[b]).astype(np.float32)).astype(np.int64)
+    # the kernels' weight map: 16.16 fixed-point bin position -> integer interpolation inside the bin
+    q = np.floor(np.clip(binpos, 0, None).astype(np.float64) * 65536.0).astype(np.int64)
+    qb = np.minimum(q >> 16, nb)
+    lut_p = np.append(lut_h, lut_h[-1])
+    w = lut_p[qb] + (((lut_p[qb + 1] - lut_p[qb]) * (q & 0xffff)) >> 16)
     w[~kept, :] = 0
     w[:, ~kept] = 0
     np.fill_diagonal(w, 0)
@@ -263,3 +266,9 @@ def test_corr_hist_and_votes(eng, n, g):
     rel = np.abs(gd - ref_deg).max() / ref_deg.max()
     assert rel < 1e-5, f"node degree off by {rel:.2e}"
     assert np.abs(gv - ref_votes).max() / ref_votes.max() < 1e-5
+    # the rho spill (pass 1 keeps the bin positions in HBM, pass 2 streams them back) is only a
+    # different route for the same integers: none / partial / complete spill give identical sums
+    for tiles in (0, 3):
+        v2, d2, h2, _ = eng.corr_network_votes(rc, eng._i32(label), L, nbins=nb, spill_tiles=tiles)
+        torch.cuda.synchronize()
+        assert torch.equal(h2, hist) and torch.equal(v2, votes) and torch.equal(d2, degree), f"spill_tiles={tiles}"
