@@ -42,6 +42,7 @@ CONFIGS = {
     # name: (studies, cells/study, genes, types/study, description)
     "c2": (4, 50000, 2000, 10, "c2: MetaNeighborUS fast_version=False, full network, 4 studies x 50,000 cells x 2,000 HVGs, 40 clusters"),
     "c2_small": (4, 5000, 2000, 10, "c2 at 1/10 cells (dev check only)"),
+    "c2_mid": (4, 15000, 2000, 10, "c2 at 3/10 cells (profiling only)"),
 }
 REF_SAMPLE_CELLS_PER_STUDY = 1000        # CPU arm: 4 x 1,000 cells of the same generator (N^2 = 1.6e7 pairs)
 

@@ -120,7 +120,7 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  *                           over pairs i<j, i in [row0,row1), both cells kept
  * LUT   : mn_corr_lut    -- histogram -> fixed-point CDF table W = (rank-1)/max
  * Pass 2: mn_corr_vote   -- rho tiles again (or from the rho spill) -> W via LUT -> integer vote sums
- *   votes  uint64 [N, L]  sum_j W_fix(rho_ij) [label(j)==l]   (W_fix = W * 2^26; j != i)
+ *   votes  uint64 [N, L]  sum_j W_fix(rho_ij) [label(j)==l]   (W_fix = W * 2^20; j != i)
  *   degree uint64 [N]     sum_j W_fix(rho_ij)                 (j != i)
  * Both accumulate with integer atomics (exact, order-independent, so the
  * result is bit-identical for any tile schedule or GPU count).  The caller
@@ -147,7 +147,9 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
 int mn_corr_spill_layout(int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
                          int32_t nbins, int64_t* n_tiles /* host */, int64_t* tile_bytes /* host */);
 /* n_diag = number of diagonal entries (all cells, they tie at rho = 1 -- utils.py:72) */
-int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut /* [nbins+1] */,
+/* lut uint32 [nbins + 2]: lut[b] = W_fix at the lower edge of bin b, lut[nbins] = at the upper edge of the
+ * last bin, lut[nbins + 1] = 1 if some bin rises by more than 2047 (pass 2 then uses its two-load lookup) */
+int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut /* [nbins+2] */,
                 mn_stream_t stream);
 int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
                  int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,

@@ -34,8 +34,9 @@ def metaNeighborUS_fast(X, S, C, node_degree_normalization, one_vs_best, compute
     """MetaNeighborUS.py:228-306.  S, C: pandas Series (or arrays) of labels."""
     S = np.asarray(S.values if hasattr(S, "values") else S, dtype=object)
     C = np.asarray(C.values if hasattr(C, "values") else C, dtype=object)
+    Xd = engine.to_device_matrix(prepare_matrix(X))     # the upload runs while the host encodes the labels
     lay = label_layout(S, C)
-    r = engine.us_fast(prepare_matrix(X), lay, bool(node_degree_normalization), bool(one_vs_best))
+    r = engine.us_fast(Xd, lay, bool(node_degree_normalization), bool(one_vs_best))
     keep = _keep_rows(r["n_pos"])        # labels whose cells were all zero-variance vanish (:273-281)
     labels = lay.row_labels[keep]
     tab = pd.DataFrame(r["table"][np.ix_(keep, keep)], index=labels, columns=labels)
@@ -53,13 +54,14 @@ def MetaNeighborUS_from_trained(trained_model, test_data, study_col, ct_col, nod
     """MetaNeighborUS.py:391-430."""
     S = np.asarray(study_col, dtype=object)
     C = np.asarray(ct_col, dtype=object)
+    Xd = engine.to_device_matrix(prepare_matrix(test_data))     # the upload runs while the host encodes the labels
     lay = label_layout(S, C, replace_bar=True)
     cols = trained_model.columns
     cent = np.ascontiguousarray(trained_model.iloc[1:].values.T, dtype=np.float32)      # [L_train, G]
     n_cells = np.asarray(trained_model.iloc[0].values, dtype=np.float32)
     st_names = np.array([str(c).split("|")[0] for c in cols.values], dtype=object)    # :341-343
     st_uniq, st_codes = np.unique(st_names, return_inverse=True)
-    r = engine.us_pretrained(prepare_matrix(test_data), lay, cent, n_cells, st_codes.astype(np.int32), len(st_uniq),
+    r = engine.us_pretrained(Xd, lay, cent, n_cells, st_codes.astype(np.int32), len(st_uniq),
                              bool(node_degree_normalization), bool(one_vs_best))
     keep = _keep_rows(r["n_pos"])
     labels = lay.row_labels[keep]
@@ -78,8 +80,9 @@ def metaNeighborUS_default(adata, study_col, ct_col, node_degree_normalization, 
     [train label, test label] in globally sorted label order, like the reference."""
     S = np.asarray(adata.obs[study_col].values, dtype=object)
     C = np.asarray(adata.obs[ct_col].values, dtype=object)
+    Xd = engine.to_device_matrix(prepare_matrix(adata.X))     # the upload runs while the host encodes the labels
     lay = label_layout(S, C)
-    r = engine.us_default(prepare_matrix(adata.X), lay, bool(node_degree_normalization))
+    r = engine.us_default(Xd, lay, bool(node_degree_normalization))
     order = np.argsort(lay.sorted_pos)                       # row-order ids in globally sorted order
     labels = lay.row_labels[order]
     auc = r["auroc"][np.ix_(order, order)]                   # [test, train]

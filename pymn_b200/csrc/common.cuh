@@ -14,9 +14,13 @@
 namespace mn {
 
 // Fixed-point scale of the rank-standardised network weight: W_fix = W * 2^MN_W_SHIFT, W in [0, 1].
-// 26 bits keep a warp-wide sum of 32 weights inside 32 bits (one REDUX.SUM) while the resolution
-// (1.5e-8) stays far below the LUT's interpolation error.
-constexpr int MN_W_SHIFT = 26;
+// 20 bits: the resolution (9.5e-7 per pair; a vote is a sum over thousands of pairs, so the relative
+// rounding noise of a vote is ~1e-8, below float32) leaves room to pack a LUT entry -- W at the lower
+// bin edge (21 bits) and the rise across the bin (11 bits) -- into ONE 32-bit word, which halves the
+// shared-memory lookups of pass 2 (its bottleneck: random-bank LDS).
+constexpr int MN_W_SHIFT = 20;
+constexpr int MN_LUT_DELTA_BITS = 11;
+constexpr uint32_t MN_LUT_DELTA_MAX = (1u << MN_LUT_DELTA_BITS) - 1u;
 constexpr unsigned long long MN_W_ONE = 1ull << MN_W_SHIFT;
 
 // optional CSR view of the expression matrix (scipy.sparse.csr_matrix layout); indptr == nullptr = dense input

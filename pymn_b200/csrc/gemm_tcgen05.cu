@@ -199,16 +199,30 @@ __device__ __forceinline__ float rho_binpos(float acc, float inv_i_half, float i
 // cell's scale) and negative values convert to 0.  This integer is what pass 1 bins, what the rho
 // spill stores and what pass 2 maps to a weight, so the three can never disagree.
 constexpr int Q_FRAC_BITS = 16;
-__device__ __forceinline__ uint32_t rho_q(float acc, float inv_i_half, float inv_j, float half_bins) {
-    return __float2uint_rd(rho_binpos(acc, inv_i_half, inv_j, half_bins) * (float)(1 << Q_FRAC_BITS));
+__device__ __forceinline__ uint32_t rho_q(float acc, float inv_i_half, float inv_j, float half_bins, uint32_t q_top) {
+    return min(__float2uint_rd(rho_binpos(acc, inv_i_half, inv_j, half_bins) * (float)(1 << Q_FRAC_BITS)), q_top);
 }
-// W (2^MN_W_SHIFT fixed point) by linear interpolation inside the bin; tab[top + 1] == tab[top]
-__device__ __forceinline__ uint32_t w_from_q(uint32_t q, const uint32_t* tab, unsigned top) {
-    const unsigned b = min(q >> Q_FRAC_BITS, top);
-    const uint32_t lo = tab[b], hi = tab[b + 1];
+// Shared-memory copy of the LUT, one packed word per bin: (W at the lower edge) << 11 | (rise across the bin).
+// tab has nbins + 2 entries: q <= nbins << 16 may address entry nbins (rise 0), and the two-load form reads one further.
+__device__ __forceinline__ uint32_t lut_pack(const uint32_t* lut, int i, int nbins) {
+    const uint32_t lo = lut[i < nbins ? i : nbins];
+    const uint32_t hi = lut[i + 1 < nbins ? i + 1 : nbins];
+    const uint32_t d = hi - lo;
+    return (lo << MN_LUT_DELTA_BITS) | (d < MN_LUT_DELTA_MAX ? d : MN_LUT_DELTA_MAX);
+}
+// W by linear interpolation inside the bin.  One load when every bin's rise fits the 11-bit field
+// (lut[nbins + 1] == 0, the normal case); otherwise (a bin holding more than 0.2 % of all pairs: tiny
+// gene sets with heavily tied rho) `wide` selects the two-load form, which reads the next entry's edge.
+// Both forms give the same integer whenever the rise fits.
+__device__ __forceinline__ uint32_t w_from_q(uint32_t q, const uint32_t* tab) {
+    const uint32_t e = tab[q >> Q_FRAC_BITS];
+    return (e >> MN_LUT_DELTA_BITS) + (((e & MN_LUT_DELTA_MAX) * (q & ((1u << Q_FRAC_BITS) - 1u))) >> Q_FRAC_BITS);
+}
+__device__ __forceinline__ uint32_t w_from_q_wide(uint32_t q, const uint32_t* tab) {
+    const unsigned b = q >> Q_FRAC_BITS;
+    const uint32_t lo = tab[b] >> MN_LUT_DELTA_BITS, hi = tab[b + 1] >> MN_LUT_DELTA_BITS;
     return lo + __umulhi(hi - lo, q << (32 - Q_FRAC_BITS));
 }
-
 
 // ------------------------------------------------------------------ pass-2 vote accumulation
 // One thread = one row (cell i) of a tile; it walks the tile's columns in chunks of 32 fixed-point bin
@@ -240,25 +254,36 @@ struct VoteRows {
             run_acc = 0ull;
         }
     }
-    // r: 32 bin positions in, weights out.  brk: bit c set = a label run starts at column c of the chunk.
-    // vcol = &votes[(first column of the chunk) * L]
-    __device__ __forceinline__ void chunk(uint32_t (&r)[32], unsigned brk, const int32_t* s_lab_c0,
-                                          const uint32_t* s_table, unsigned top, bool sym,
-                                          unsigned long long* vcol, int L, uint64_t pol_ef, uint32_t* colw_c0,
-                                          int lane) {
+    // r: 32 bin positions in, weights out.  brk: bit c set = a label run starts at column c of the chunk;
+    // labs.at(c) = label of column c of the chunk.  vcol = &votes[(first column of the chunk) * L].
+    // Returns in lane l the sum of column l over the warp's 32 rows when the rows share one label
+    // (otherwise 0: the mixed-label columns have been flushed to global memory already).
+    template <typename LabSrc>
+    __device__ __forceinline__ uint32_t chunk(uint32_t (&r)[32], unsigned brk, const LabSrc labs,
+                                              const uint32_t* s_table, bool wide, bool sym,
+                                              unsigned long long* vcol, int L, uint64_t pol_ef, int lane) {
         uint32_t mycol = 0u;
         if (brk & 1u) {                                  // warp-uniform: a label run starts with this chunk
             flush();
-            cur_lab = s_lab_c0[0];
+            cur_lab = labs.at(0);
         }
         if ((brk >> 1) == 0u) {
             // fast path (almost every chunk): one label run -> branch-free
-            uint32_t acc32 = 0u;                         // 32 weights <= 2^26 each fit 32 bits
+            uint32_t acc32 = 0u;                         // 32 weights <= 2^20 each fit 32 bits
+            if (!wide) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const uint32_t w = w_from_q(r[c], s_table, top);
-                acc32 += w;
-                r[c] = w;
+                for (int c = 0; c < 32; ++c) {
+                    const uint32_t w = w_from_q(r[c], s_table);
+                    acc32 += w;
+                    r[c] = w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const uint32_t w = w_from_q_wide(r[c], s_table);
+                    acc32 += w;
+                    r[c] = w;
+                }
             }
             run_acc += acc32;
         } else {
@@ -266,9 +291,9 @@ struct VoteRows {
             for (int c = 0; c < 32; ++c) {
                 if (c > 0 && (brk & (1u << c))) {
                     flush();
-                    cur_lab = s_lab_c0[c];
+                    cur_lab = labs.at(c);
                 }
-                const uint32_t w = w_from_q(r[c], s_table, top);
+                const uint32_t w = wide ? w_from_q_wide(r[c], s_table) : w_from_q(r[c], s_table);
                 run_acc += w;
                 r[c] = w;
             }
@@ -276,7 +301,7 @@ struct VoteRows {
         if (sym) {
             if (warp_uniform) {
                 // 32 x 32 transpose-reduce: 31 shuffles leave in lane l the sum over the warp's
-                // 32 rows of column l of the chunk  (<= 32 * 2^26, fits 32 bits)
+                // 32 rows of column l of the chunk  (<= 32 * 2^20, fits 32 bits)
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     const bool up = (lane & off) != 0;
@@ -295,10 +320,19 @@ struct VoteRows {
                     if (grp_leader && s) red_add_u64_hint(vcol + (int64_t)c * L + lab_i, (unsigned long long)s, pol_ef);
                 }
             }
-            colw_c0[lane] = mycol;
         }
+        return mycol;
     }
     __device__ __forceinline__ void finish() { flush(); }
+};
+// column labels of a chunk: staged in shared memory / one per lane in a register
+struct SmemLabels {
+    const int32_t* p;
+    __device__ __forceinline__ int at(int c) const { return p[c]; }
+};
+struct LaneLabels {
+    int v;
+    __device__ __forceinline__ int at(int c) const { return __shfl_sync(0xffffffffu, v, c); }
 };
 
 // Column side of one tile: s_colw [EPI_WARPS][BN/2] per-warp column sums (warps 0-3 = first half of the
@@ -467,7 +501,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (EPI != EPI_STORE) {
         // hist starts at zero; lut is copied in
         for (int i = threadIdx.x; i < p.nbins + 2; i += GEMM_THREADS)
-            s_table[i] = (EPI == EPI_VOTE) ? p.lut[i < p.nbins ? i : p.nbins] : 0u;
+            s_table[i] = (EPI == EPI_VOTE) ? lut_pack(p.lut, i, p.nbins) : 0u;
     }
     tc_fence_before();
     __syncthreads();
@@ -636,7 +670,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 }
             } else if (EPI == EPI_HIST) {
                 const float inv_i_half = inv_i * half_bins;
-                const unsigned top = (unsigned)p.nbins, sink = (unsigned)p.nbins + 1u;
+                const unsigned sink = (unsigned)p.nbins + 1u;
+                const uint32_t q_top = (uint32_t)p.nbins << Q_FRAC_BITS;
                 const bool row_live = inv_i > 0.f;
                 // rho spill: this warp's 32 x 32 chunks in tile-native order, [ew][chunk][k][lane] x 16 B
                 // (coalesced 512-byte stores); masked entries are stored as 0, which maps to W = lut[0] = 0
@@ -652,18 +687,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float inv_j = s_invb[c0 + c];
-                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins, q_top);
                                 const bool use = inv_j > 0.f;
-                                atomicAdd(&s_table[use ? min(qv >> Q_FRAC_BITS, top) : sink], 1u);
+                                atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
                                 r[c] = use ? qv : 0u;
                             }
                         } else {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) {
                                 const float inv_j = s_invb[c0 + c];
-                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins);
+                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins, q_top);
                                 const bool use = inv_j > 0.f && (n0 + c0 + c > m);
-                                atomicAdd(&s_table[use ? min(qv >> Q_FRAC_BITS, top) : sink], 1u);
+                                atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
                                 r[c] = use ? qv : 0u;
                             }
                         }
@@ -687,6 +722,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const float qnan = __int_as_float(0x7fc00000);
                 const float inv_i_half = (inv_i > 0.f) ? inv_i * half_bins : qnan;
                 const bool sym = p.tri != 0;
+                const uint32_t q_top = (uint32_t)p.nbins << Q_FRAC_BITS;
+                const bool wide = p.lut[p.nbins + 1] != 0u;
                 VoteRows vr;
                 vr.begin(p.label[row_ok ? m : p.M - 1], p.votes + (row_ok ? m : 0) * (int64_t)p.L, lane);
                 uint32_t* colw = s_colw + ew * HALF_COLS;
@@ -697,17 +734,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     if (!diag_tile) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
-                            r[c] = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
+                            r[c] = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins, q_top);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins);
+                            const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins, q_top);
                             const bool use = sym ? (n0 + c0 + c > m) : (n0 + c0 + c != m);
                             r[c] = use ? qv : 0u;
                         }
                     }
-                    vr.chunk(r, s_flush[c0 >> 5], s_lab + c0, s_table, (unsigned)p.nbins, sym,
-                             p.votes + (n0 + c0) * (int64_t)p.L, p.L, pol_ef, colw + (c0 - cbeg), lane);
+                    const uint32_t mycol = vr.chunk(r, s_flush[c0 >> 5], SmemLabels{s_lab + c0}, s_table, wide,
+                                                    sym, p.votes + (n0 + c0) * (int64_t)p.L, p.L, pol_ef, lane);
+                    if (sym) colw[c0 - cbeg + lane] = mycol;
                 }
                 vr.finish();
                 if (sym && lane == 0) s_wlab[ew] = vr.warp_uniform ? vr.lab_i : -2;
@@ -746,98 +784,135 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
 // ------------------------------------------------------------------ pass 2 from the rho spill
 // Streams the bin positions pass 1 left in HBM (tile-native layout, see EPI_HIST) instead of
-// recomputing the tiles on the tensor cores: an HBM-bound kernel, 4 B per cell pair.  One CTA of
-// 8 warps plays the 8 epilogue warps of the GEMM kernel on one tile at a time (same thread <-> (row,
-// column) mapping, same VoteRows arithmetic, hence bit-identical vote sums); CTAs take blocks of
-// `tb` consecutive tiles round-robin, and every warp keeps its next 4 KB chunk in flight in
-// registers while it works on the current one.
+// recomputing the tiles on the tensor cores: an HBM-bound kernel, 4 B per cell pair.  Same VoteRows
+// arithmetic as the GEMM epilogue, hence bit-identical vote sums.
+// Every warp works on its own: it owns one 32-row quarter of `tb` consecutive tiles of the linear tile
+// order (same column tile, consecutive row tiles inside a band) and walks all 256 columns of each tile,
+// so that
+//   - a row's running sum is flushed once per label run of the whole tile row (one 64-bit atomic per row
+//     and tile),
+//   - the column sums stay in registers across the run of tiles and are flushed when the column tile
+//     or the rows' label changes (one 64-bit reduction per column and ~tb tiles),
+//   - no barrier and no shared memory besides the LUT is needed.
+// The next 4 KB chunk is kept in flight in registers while the current one is processed.
+constexpr int SPILL_WARPS = 16;
 template <int BN>
-__global__ void __launch_bounds__(EPI_THREADS, 2) vote_spill_kernel(const GemmParams p, int tb) {
+__global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const GemmParams p, int tb) {
     extern __shared__ __align__(16) uint32_t s_dyn[];
     constexpr int HALF_COLS = BN / 2;
-    constexpr int NCH = HALF_COLS / 32;
-    uint32_t* s_table = s_dyn;                                             // [nbins + 2]
-    const int table_words = (p.nbins + 2 + 3) & ~3;
-    int32_t* s_lab = reinterpret_cast<int32_t*>(s_table + table_words);    // [BN]
-    uint32_t* s_flush = reinterpret_cast<uint32_t*>(s_lab + BN);           // [BN / 32]
-    uint32_t* s_colw = s_flush + BN / 32;                                  // [EPI_WARPS][BN / 2]
-    int32_t* s_wlab = reinterpret_cast<int32_t*>(s_colw + EPI_WARPS * HALF_COLS);   // [EPI_WARPS]
+    constexpr int NCH = HALF_COLS / 32;         // chunks per column half
+    constexpr int NCK = 2 * NCH;                // chunks per tile row
+    uint32_t* s_table = s_dyn;                  // [nbins + 2]
+    for (int i = threadIdx.x; i < p.nbins + 2; i += blockDim.x) s_table[i] = lut_pack(p.lut, i, p.nbins);
+    const bool wide = p.lut[p.nbins + 1] != 0u;
+    __syncthreads();
 
-    for (int i = threadIdx.x; i < p.nbins + 2; i += EPI_THREADS) s_table[i] = p.lut[i < p.nbins ? i : p.nbins];
-
-    const int ew = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int et = threadIdx.x;
-    const int row_in_tile = ((ew + 2) & 3) * 32 + lane;      // the GEMM's epilogue warp ew is CTA warp ew + 2
-    const int cbeg = (ew >> 2) * HALF_COLS;
-    const uint64_t pol_ef = l2_evict_first_policy();
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (int)blockDim.x >> 5;
+    const int gw = blockIdx.x * n_warps + (threadIdx.x >> 5);
+    const int quarter = gw & 3;                                  // rows quarter * 32 .. + 31 of every tile
+    const int role0 = (quarter + 2) & 3;                         // GEMM epilogue warp (ew) that wrote them, column half 0
     const int n_blocks = (p.spill_tiles + tb - 1) / tb;
-    const uint4* base = reinterpret_cast<const uint4*>(p.spill) + (size_t)(ew * NCH) * 256 + lane;
+    const int blk_step = ((int)gridDim.x * n_warps) >> 2;
+    const uint64_t pol_ef = l2_evict_first_policy();
     constexpr size_t TILE_V4 = (size_t)BM * BN / 4;
+    // uint4 index of (tile, chunk k of the tile row): role = role0 + 4 * (k / NCH), chunk-in-role = k % NCH
+    const uint4* base = reinterpret_cast<const uint4*>(p.spill) + lane;
+    auto chunk_src = [&](int tile, int k) {
+        return base + (size_t)tile * TILE_V4 + (size_t)(((role0 + 4 * (k / NCH)) * NCH + (k % NCH)) * 256);
+    };
 
     TileIter it;
     it.init(p, BN, 0);
     int cur_tile = 0;
     uint4 nx[8];
-    int blk = blockIdx.x;
+    int blk = gw >> 2;
     if (blk < n_blocks) {
-        const uint4* src = base + (size_t)(blk * tb) * TILE_V4;
+        const uint4* src = chunk_src(blk * tb, 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) nx[k] = __ldcs(src + k * 32);
     }
-    for (; blk < n_blocks; blk += gridDim.x) {
+    // column side carried across tiles
+    unsigned long long colacc[NCK];
+#pragma unroll
+    for (int k = 0; k < NCK; ++k) colacc[k] = 0ull;
+    int64_t col_n0 = -1;
+    int col_lab = 0;
+    int lab_c[NCK];                  // label of column n0 + 32 k + lane
+#pragma unroll
+    for (int k = 0; k < NCK; ++k) lab_c[k] = 0;
+    int64_t lab_n0 = -1;
+
+    auto flush_cols = [&]() {
+        if (col_n0 >= 0) {
+#pragma unroll
+            for (int k = 0; k < NCK; ++k) {
+                if (colacc[k]) red_add_u64_hint(p.votes + (col_n0 + 32 * k + lane) * (int64_t)p.L + col_lab, colacc[k], pol_ef);
+                colacc[k] = 0ull;
+            }
+        }
+        col_n0 = -1;
+    };
+
+    for (; blk < n_blocks; blk += blk_step) {
         const int t_end = min(p.spill_tiles, (blk + 1) * tb);
         for (int tile = blk * tb; tile < t_end; ++tile) {
             it.advance(tile - cur_tile);
             cur_tile = tile;
             const int64_t m0 = (int64_t)it.mt * BM, n0 = (int64_t)it.nt() * BN;
-            const int64_t m = m0 + row_in_tile;
-            for (int c = et; c < BN; c += EPI_THREADS) {
-                const int64_t n = n0 + c;
-                const bool ok = n < p.N;
-                const int lab = ok ? p.label[n] : 0;
-                s_lab[c] = lab;
-                const bool brk = (c == 0) || (c == HALF_COLS) || !ok || (n >= 1 && p.label[n - 1] != lab);
-                const unsigned msk = __ballot_sync(0xffffffffu, brk);
-                if (lane == 0) s_flush[c >> 5] = msk;
-            }
-            __syncthreads();          // metadata staged; the previous tile's column merge has been read
+            const int64_t m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
+            if (n0 != lab_n0) {
+#pragma unroll
+                for (int k = 0; k < NCK; ++k) {
+                    const int64_t n = n0 + 32 * k + lane;
+                    lab_c[k] = n < p.N ? p.label[n] : -1 - k;       // columns past the end: a run of their own (zero weights)
+                }
+                lab_n0 = n0;
+            }
             VoteRows vr;
             vr.begin(p.label[row_ok ? m : p.M - 1], p.votes + (row_ok ? m : 0) * (int64_t)p.L, lane);
-            uint32_t* colw = s_colw + ew * HALF_COLS;
+            if (col_n0 >= 0 && (col_n0 != n0 || col_lab != vr.lab_i || !vr.warp_uniform)) flush_cols();
+            if (vr.warp_uniform) {
+                col_n0 = n0;
+                col_lab = vr.lab_i;
+            }
 #pragma unroll
-            for (int ci = 0; ci < NCH; ++ci) {
+            for (int k = 0; k < NCK; ++k) {
                 uint32_t r[32];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    r[4 * k] = nx[k].x;
-                    r[4 * k + 1] = nx[k].y;
-                    r[4 * k + 2] = nx[k].z;
-                    r[4 * k + 3] = nx[k].w;
+                for (int j = 0; j < 8; ++j) {
+                    r[4 * j] = nx[j].x;
+                    r[4 * j + 1] = nx[j].y;
+                    r[4 * j + 2] = nx[j].z;
+                    r[4 * j + 3] = nx[j].w;
                 }
-                // next chunk of this warp: same tile, next tile of the block, or the first tile of the
-                // CTA's next block
-                int nt_tile = tile, nci = ci + 1;
-                if (nci == NCH) {
-                    nci = 0;
+                // this warp's next chunk: same tile, next tile of the block, or the first tile of its next block
+                int nt_tile = tile, nk = k + 1;
+                if (nk == NCK) {
+                    nk = 0;
                     nt_tile = tile + 1;
-                    if (nt_tile == t_end) nt_tile = (blk + (int)gridDim.x < n_blocks) ? (blk + (int)gridDim.x) * tb : -1;
+                    if (nt_tile == t_end) nt_tile = (blk + blk_step < n_blocks) ? (blk + blk_step) * tb : -1;
                 }
                 if (nt_tile >= 0) {
-                    const uint4* src = base + (size_t)nt_tile * TILE_V4 + (size_t)nci * 256;
+                    const uint4* src = chunk_src(nt_tile, nk);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) nx[k] = __ldcs(src + k * 32);
+                    for (int j = 0; j < 8; ++j) nx[j] = __ldcs(src + j * 32);
                 }
-                const int c0 = cbeg + ci * 32;
-                vr.chunk(r, s_flush[c0 >> 5], s_lab + c0, s_table, (unsigned)p.nbins, true,
-                         p.votes + (n0 + c0) * (int64_t)p.L, p.L, pol_ef, colw + ci * 32, lane);
+                // label runs of this chunk's columns: a run starts where the label differs from the previous column's
+                int prev = __shfl_up_sync(0xffffffffu, lab_c[k], 1);
+                const int prev_chunk_last = __shfl_sync(0xffffffffu, lab_c[k > 0 ? k - 1 : 0], 31);
+                if (lane == 0) prev = prev_chunk_last;
+                const unsigned brk = __ballot_sync(0xffffffffu, (k == 0 && lane == 0) || prev != lab_c[k]);
+                const int lab_use = lab_c[k] < 0 ? 0 : lab_c[k];
+                const uint32_t mycol = vr.chunk(r, brk, LaneLabels{lab_use}, s_table, wide, true,
+                                                p.votes + (n0 + 32 * k) * (int64_t)p.L, p.L, pol_ef, lane);
+                colacc[k] += mycol;
             }
             vr.finish();
-            if (lane == 0) s_wlab[ew] = vr.warp_uniform ? vr.lab_i : -2;
-            __syncthreads();
-            vote_merge_columns<BN>(s_colw, s_wlab, p.votes, n0, p.L, pol_ef, ew, lane, false);
         }
     }
+    flush_cols();
 }
 
 // ------------------------------------------------------------------ CDF LUT
@@ -878,6 +953,16 @@ __global__ void corr_lut_kernel(const unsigned long long* __restrict__ hist, int
         run += hist[b];
     }
     if (tid == 0) lut[nbins] = (uint32_t)fmin(one, rint(2.0 * total * scale));
+    // lut[nbins + 1]: does some bin rise by more than the packed LUT's 11-bit field holds?
+    __syncthreads();
+    __shared__ int s_wide;
+    if (tid == 0) s_wide = 0;
+    __syncthreads();
+    int widef = 0;
+    for (int b = b0; b < b1; ++b) widef |= (lut[b + 1] - lut[b] > MN_LUT_DELTA_MAX) ? 1 : 0;
+    if (widef) atomicOr(&s_wide, 1);
+    __syncthreads();
+    if (tid == 0) lut[nbins + 1] = (uint32_t)s_wide;
 }
 
 __global__ void vote_rowsum_kernel(const unsigned long long* __restrict__ votes, int64_t N, int L,
@@ -981,24 +1066,27 @@ static int64_t corr_tile_count(int64_t N, int64_t row0, int64_t row1, int shard_
 
 template <int BN>
 static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)((p.nbins + 2 + 3) & ~3) * 4 + (size_t)BN * 4 + (BN / 32) * 4 +
-                        (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4;
+    const size_t smem = (size_t)((p.nbins + 2 + 3) & ~3) * 4;
     auto kern = vote_spill_kernel<BN>;
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int tb = 8;
+    int warps = SPILL_WARPS;
+    if (const char* e = getenv("MN_SPILL_WARPS")) {    // experiment knob (multiple of 4)
+        const int v = atoi(e);
+        if (v >= 4 && v <= SPILL_WARPS && (v & 3) == 0) warps = v;
+    }
+    // tiles per run: the column sums are flushed about once per run, so long runs are cheaper (64 = one
+    // column segment of a band), but every warp should still get >= 8 runs to balance the grid
+    int tb = (int)(((long long)p.spill_tiles * 4) / (8ll * sm_count() * warps));
+    tb = tb < 1 ? 1 : (tb > 64 ? 64 : tb);
     if (const char* e = getenv("MN_SPILL_TB")) {       // tuning knob
         const int v = atoi(e);
         if (v > 0) tb = v;
     }
-    int per_sm = 2;
-    if (const char* e = getenv("MN_SPILL_CTAS")) {
-        const int v = atoi(e);
-        if (v > 0) per_sm = v;
-    }
     const int n_blocks = (p.spill_tiles + tb - 1) / tb;
-    int grid = sm_count() * per_sm;
-    if (n_blocks < grid) grid = n_blocks;
-    kern<<<grid, EPI_THREADS, smem, st>>>(p, tb);
+    int grid = sm_count();
+    const int want = (n_blocks * 4 + warps - 1) / warps;     // one warp per (run, row quarter)
+    if (want < grid) grid = want;
+    kern<<<grid, warps * 32, smem, st>>>(p, tb);
     MN_LAUNCH_CHECK();
     return 0;
 }

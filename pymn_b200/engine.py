@@ -350,7 +350,7 @@ def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAU
               spill, n_sp)
     if reduce_fn is not None:
         reduce_fn(hist)
-    lut = torch.empty((nbins + 1,), dtype=torch.int32, device=dev)
+    lut = torch.empty((nbins + 2,), dtype=torch.int32, device=dev)
     _lib.call("mn_corr_lut", hist, nbins, N, lut)
     votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
     degree = torch.zeros((N,), dtype=torch.int64, device=dev)
@@ -418,7 +418,7 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
     if t: t.stop("corr_hist")
     if reduce_fn is not None:
         reduce_fn(hist)
-    lut = torch.empty((nbins + 1,), dtype=torch.int32, device=dev)
+    lut = torch.empty((nbins + 2,), dtype=torch.int32, device=dev)
     _lib.call("mn_corr_lut", hist, nbins, N, lut)
     votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
     degree = torch.zeros((N,), dtype=torch.int64, device=dev)

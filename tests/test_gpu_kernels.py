@@ -248,8 +248,8 @@ def test_corr_hist_and_votes(eng, n, g):
     assert np.abs(np.cumsum(got_hist - ref_hist)).max() <= max(4, 2e-3 * ref_hist.sum())
     if g * g * g < (1 << 24):
         assert np.array_equal(got_hist, ref_hist), "all partial sums are exact integers < 2^24: histogram must be exact"
-    lut_h = lut.cpu().numpy().astype(np.int64)
-    assert np.all(np.diff(lut_h) >= 0) and lut_h[0] == 0 and lut_h[-1] <= (1 << 26)
+    lut_h = lut.cpu().numpy().astype(np.int64)[:nb + 1]
+    assert np.all(np.diff(lut_h) >= 0) and lut_h[0] == 0 and lut_h[-1] <= (1 << 20)
     # the kernels' weight map: 16.16 fixed-point bin position -> integer interpolation inside the bin
     q = np.floor(np.clip(binpos, 0, None).astype(np.float64) * 65536.0).astype(np.int64)
     qb = np.minimum(q >> 16, nb)
