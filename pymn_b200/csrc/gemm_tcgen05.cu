@@ -77,6 +77,8 @@ struct GemmParams {
     uint32_t* spill;
     int spill_tiles;
     int tile_base;           // first linear tile index of this launch (pass 2 over the tiles that were not spilled)
+    int ctas;                // 1, or 2 = CTA pairs (cta_group::2): a tile is 256 rows, mt counts 256-row tiles,
+                             //    CTA r of the pair owns rows [128 r, 128 r + 128) of it
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -119,6 +121,70 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster sit on the two SMs of one TPC
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_remote_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait on a barrier that a thread of the peer CTA arrives on after writing data into this CTA's shared memory
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait_cluster(addr, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(addr, parity)) {
+        if (clock64() - t0 > 20000000000ll) {
+            printf("pymn_b200 gemm: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are counted on the LEADER CTA's barrier
+// (same shared-memory offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -376,7 +442,7 @@ __device__ __forceinline__ void vote_merge_columns(const uint32_t* s_colw, const
 // instead of once per row tile.  In `tri` mode only tiles holding some column index > some row index
 // exist:  mt * BM < (nt + 1) * bn.
 struct TileIter {
-    int mt0, mt_step, n_my, band, n_tiles, tri, bn;
+    int mt0, mt_step, n_my, band, n_tiles, tri, bn, bm;
     int k0, nt_, r, mt;
     bool ok;
     __device__ __forceinline__ int mt_of(int k) const { return mt0 + k * mt_step; }
@@ -384,17 +450,18 @@ struct TileIter {
         const int v = n_my - k0;
         return v < band ? v : band;
     }
-    __device__ __forceinline__ int first_nt_of_band() const { return tri ? (mt_of(k0) * BM) / bn : 0; }
+    __device__ __forceinline__ int first_nt_of_band() const { return tri ? (mt_of(k0) * bm) / bn : 0; }
     __device__ __forceinline__ int col_len() const {
         const int rows = rows_in_band();
         if (!tri) return rows;
-        const int max_mt = ((nt_ + 1) * bn - 1) / BM;
+        const int max_mt = ((nt_ + 1) * bn - 1) / bm;
         if (max_mt < mt0) return 0;
         const int cnt = (max_mt - mt0) / mt_step + 1 - k0;
         return cnt < 0 ? 0 : (cnt < rows ? cnt : rows);
     }
     __device__ __forceinline__ void init(const GemmParams& p, int bn_, int start) {
         mt0 = p.mt0; mt_step = p.mt_step; band = p.band; n_tiles = p.n_tiles; tri = p.tri; bn = bn_;
+        bm = BM * p.ctas;
         n_my = p.mt1 > p.mt0 ? (p.mt1 - p.mt0 + p.mt_step - 1) / p.mt_step : 0;
         k0 = 0; r = 0; mt = mt0;
         ok = n_my > 0 && n_tiles > 0;
@@ -429,15 +496,26 @@ struct TileIter {
 };
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int EPI, int NCHAIN>
+// CTAS = 2: CTA pairs (clusters of two CTAs on the two SMs of a TPC) work on 256 x BN tiles with
+// tcgen05.mma.cta_group::2 (M = 256).  CTA r loads its own 128 rows of A and only HALF of the B tile
+// (BN / 2 rows); the tensor cores of both SMs read both halves.  Per SM and k-block that is 32 KB
+// written + 32 KB read of shared memory instead of 48 + 48 KB -- the single-CTA form needs 96 B/clk of
+// the 128 B/clk shared-memory bandwidth for the MMA reads alone and tops out near 2/3 of the tensor
+// peak once TMA writes and the epilogue's lookups share the same pipe.  Only the leader (rank 0)
+// claims tiles and issues MMAs; completion is multicast to the barriers of both CTAs.
+template <int BN, int EPI, int NCHAIN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
             const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr bool PAIR = (CTAS == 2);
+    constexpr int B_ROWS = BN / CTAS;              // rows of the B tile this CTA stages
     constexpr uint32_t A_BYTES = BM * BK * 2;
-    constexpr uint32_t B_BYTES = BN * BK * 2;
+    constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0u;
     // NCHAIN independent accumulators per tile (k-blocks dealt round-robin, summed in FP32 by the
     // epilogue): the tensor core truncates when it adds into a long FP32 chain, so shorter chains
     // cut the accumulation bias NCHAIN-fold.  Two tiles in flight when TMEM (512 columns) allows.
@@ -486,17 +564,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], EPI_WARPS);
+            mbar_init(&tempty_bar[a], EPI_WARPS * CTAS);   // the leader's MMA thread waits for the epilogues of both CTAs
         }
         for (int qi = 0; qi < TQ; ++qi) {
             mbar_init(&qfull_bar[qi], 1);
-            mbar_init(&qempty_bar[qi], 1 + EPI_WARPS);     // MMA thread + one lane of every epilogue warp
+            // leader: MMA thread + one lane of every epilogue warp (+ the peer's producer and epilogue warps)
+            mbar_init(&qempty_bar[qi], 1 + EPI_WARPS + (PAIR ? 1 + EPI_WARPS : 0));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (EPI != EPI_STORE) {
         // hist starts at zero; lut is copied in
@@ -505,8 +589,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();        // the peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    // where the consumers of this CTA hand queue slots / accumulator stages back: the leader's barriers
+    auto arrive_leader = [&](uint64_t* bar) {
+        if constexpr (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(bar), 0u));
+        else mbar_arrive(bar);
+    };
+    auto wait_queue = [&](uint64_t* bar, uint32_t parity) {
+        if constexpr (PAIR) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -522,11 +616,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             int s = 0, qs = 0;
             uint32_t ph = 0, qph = 0;
             for (;;) {
-                mbar_wait(&qempty_bar[qs], qph ^ 1u);
-                const unsigned int t = atomicAdd(p.tile_counter, 1u) + (unsigned int)p.tile_base;
-                const int tile = (t < (unsigned int)p.total_tiles) ? (int)t : -1;
-                s_tileq[qs] = tile;
-                mbar_arrive(&qfull_bar[qs]);
+                int tile;
+                if (leader) {
+                    mbar_wait(&qempty_bar[qs], qph ^ 1u);
+                    const unsigned int t = atomicAdd(p.tile_counter, 1u) + (unsigned int)p.tile_base;
+                    tile = (t < (unsigned int)p.total_tiles) ? (int)t : -1;
+                    s_tileq[qs] = tile;
+                    mbar_arrive(&qfull_bar[qs]);
+                    if constexpr (PAIR) {          // ... and into the peer CTA's copy of the queue
+                        st_remote_u32(mapa_u32(smem_u32(&s_tileq[qs]), 1u), (uint32_t)tile);
+                        mbar_arrive_remote(mapa_u32(smem_u32(&qfull_bar[qs]), 1u));
+                    }
+                } else {
+                    wait_queue(&qfull_bar[qs], qph);
+                    tile = s_tileq[qs];
+                    arrive_leader(&qempty_bar[qs]);
+                }
                 if (++qs == TQ) {
                     qs = 0;
                     qph ^= 1u;
@@ -534,16 +639,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (tile < 0) break;
                 it.advance(tile - cur_tile);
                 cur_tile = tile;
-                const int m0 = it.mt * BM, n0 = it.nt() * BN;
+                const int m0 = it.mt * (BM * CTAS) + (int)cta_rank * BM, n0 = it.nt() * BN + (int)cta_rank * B_ROWS;
                 for (int term = 0; term < p.n_terms; ++term) {
                     const CUtensorMap* ma = p.a_sel[term] ? &tm_a_lo : &tm_a_hi;
                     const CUtensorMap* mb = p.b_sel[term] ? &tm_b_lo : &tm_b_hi;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         unsigned char* sa = ring + (size_t)s * STAGE_BYTES;
-                        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                        tma_load_2d(sa, ma, &full_bar[s], kb * BK, m0);
-                        tma_load_2d(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                        if constexpr (PAIR) {
+                            if (leader) mbar_expect_tx(&full_bar[s], STAGE_BYTES * CTAS);
+                            tma_load_2d_pair(sa, ma, &full_bar[s], kb * BK, m0);
+                            tma_load_2d_pair(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                        } else {
+                            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                            tma_load_2d(sa, ma, &full_bar[s], kb * BK, m0);
+                            tma_load_2d(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                        }
                         if (++s == p.stages) {
                             s = 0;
                             ph ^= 1u;
@@ -554,8 +665,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(BM, BN);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc(BM * CTAS, BN);
             int s = 0, a = 0, qs = 0;
             uint32_t ph = 0, aph = 0, qph = 0;
             for (;;) {
@@ -579,16 +690,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance the start address by k * 16 elements * 2 B = 32 B = 2 (16-byte units)
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                   (i >= NCHAIN || k > 0) ? 1u : 0u);
+                        if constexpr (PAIR)
+                            tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                            (i >= NCHAIN || k > 0) ? 1u : 0u);
+                        else
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                       (i >= NCHAIN || k > 0) ? 1u : 0u);
                     }
-                    tc_commit(&empty_bar[s]);      // frees the smem slot once these MMAs retire
+                    // frees the smem slot (of both CTAs) once these MMAs retire
+                    if constexpr (PAIR) tc_commit_pair(&empty_bar[s]);
+                    else tc_commit(&empty_bar[s]);
                     if (++s == p.stages) {
                         s = 0;
                         ph ^= 1u;
                     }
                 }
-                tc_commit(&tfull_bar[a]);          // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if constexpr (PAIR) tc_commit_pair(&tfull_bar[a]);
+                else tc_commit(&tfull_bar[a]);
                 if (++a == ACC_STAGES) {
                     a = 0;
                     aph ^= 1u;
@@ -612,10 +731,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         const float half_bins = 0.5f * (float)p.nbins;
         const uint64_t pol_ef = l2_evict_first_policy();
         for (;;) {
-            mbar_wait(&qfull_bar[qs], qph);
+            wait_queue(&qfull_bar[qs], qph);
             const int tile = s_tileq[qs];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&qempty_bar[qs]);
+            if (lane == 0) arrive_leader(&qempty_bar[qs]);
             if (++qs == TQ) {
                 qs = 0;
                 qph ^= 1u;
@@ -623,7 +742,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             if (tile < 0) break;
             it.advance(tile - cur_tile);
             cur_tile = tile;
-            const int64_t m0 = (int64_t)it.mt * BM, n0 = (int64_t)it.nt() * BN;
+            const int64_t m0 = (int64_t)it.mt * (BM * CTAS) + (int64_t)cta_rank * BM, n0 = (int64_t)it.nt() * BN;
             const int64_t m = m0 + row_in_tile;
             // stage per-column metadata of this tile
             epi_bar_sync();                           // previous tile's readers are done
@@ -675,8 +794,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const bool row_live = inv_i > 0.f;
                 // rho spill: this warp's 32 x 32 chunks in tile-native order, [ew][chunk][k][lane] x 16 B
                 // (coalesced 512-byte stores); masked entries are stored as 0, which maps to W = lut[0] = 0
-                const bool do_spill = p.spill != nullptr && tile < p.spill_tiles;
-                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)tile * (size_t)(BM * BN)) +
+                // (a pair's 256-row tile is stored as two 128-row tiles: 2 * tile + rank)
+                const int sp_tile = tile * CTAS + (int)cta_rank;
+                const bool do_spill = p.spill != nullptr && sp_tile < p.spill_tiles;
+                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)sp_tile * (size_t)(BM * BN)) +
                             (size_t)(ew * (HALF_COLS / 32)) * 256 + lane;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
@@ -754,7 +875,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             // the accumulator stage is drained: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            if (lane == 0) arrive_leader(&tempty_bar[a]);
             if (++a == ACC_STAGES) {
                 a = 0;
                 aph ^= 1u;
@@ -776,9 +897,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();        // nobody leaves (or frees TMEM) while the peer may still signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -857,9 +982,11 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
     for (; blk < n_blocks; blk += blk_step) {
         const int t_end = min(p.spill_tiles, (blk + 1) * tb);
         for (int tile = blk * tb; tile < t_end; ++tile) {
-            it.advance(tile - cur_tile);
-            cur_tile = tile;
-            const int64_t m0 = (int64_t)it.mt * BM, n0 = (int64_t)it.nt() * BN;
+            // stored tile -> (tile of the GEMM's schedule, CTA rank inside a pair)
+            const int gt = tile / p.ctas, gr = tile - gt * p.ctas;
+            it.advance(gt - cur_tile);
+            cur_tile = gt;
+            const int64_t m0 = (int64_t)it.mt * (BM * p.ctas) + (int64_t)gr * BM, n0 = (int64_t)it.nt() * BN;
             const int64_t m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
             if (n0 != lab_n0) {
@@ -1053,16 +1180,20 @@ static int gemm_band() {
 }
 
 // number of tiles of the triangular passes for one shard (the linear tile order of TileIter)
-static int64_t corr_tile_count(int64_t N, int64_t row0, int64_t row1, int shard_rank, int shard_world, int bn) {
+// (bm = rows per tile: 128, or 256 for CTA pairs)
+static int64_t corr_tile_count(int64_t N, int64_t row0, int64_t row1, int shard_rank, int shard_world, int bn, int bm) {
     const int n_tiles = (int)((N + bn - 1) / bn);
-    const int mt1 = (int)((row1 + BM - 1) / BM);
+    const int mt1 = (int)((row1 + bm - 1) / bm);
     int64_t tiles = 0;
-    for (int mt = (int)(row0 / BM) + shard_rank; mt < mt1; mt += shard_world) {
-        const int first = (mt * BM) / bn;
+    for (int mt = (int)(row0 / bm) + shard_rank; mt < mt1; mt += shard_world) {
+        const int first = (mt * bm) / bn;
         if (first < n_tiles) tiles += n_tiles - first;
     }
     return tiles;
 }
+
+// CTA pairs (cta_group::2) for the two network passes unless MN_GEMM_1CTA is set (debugging aid)
+static int corr_ctas(bool wide) { return (wide && !getenv("MN_GEMM_1CTA")) ? 2 : 1; }
 
 template <int BN>
 static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
@@ -1091,7 +1222,7 @@ static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <int BN, int EPI, int NCHAIN>
+template <int BN, int EPI, int NCHAIN, int CTAS = 1>
 static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, const __half* b_hi,
                        const __half* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -1099,14 +1230,15 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     int rc;
     if ((rc = make_map(&ta_hi, a_hi, M, cols_a, lda, BM))) return rc;
     if ((rc = make_map(&ta_lo, a_lo ? a_lo : a_hi, M, cols_a, lda, BM))) return rc;
-    if ((rc = make_map(&tb_hi, b_hi, N, cols_b, ldb, BN))) return rc;
-    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, N, cols_b, ldb, BN))) return rc;
+    if ((rc = make_map(&tb_hi, b_hi, N, cols_b, ldb, BN / CTAS))) return rc;
+    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, N, cols_b, ldb, BN / CTAS))) return rc;
     p.M = M;
     p.N = N;
+    p.ctas = CTAS;
     p.k_blocks = (G + BK - 1) / BK;
     p.n_tiles = (int)((N + BN - 1) / BN);
-    if (p.band <= 0) p.band = gemm_band();
-    const size_t stage_bytes = (size_t)(BM + BN) * BK * 2;
+    if (p.band <= 0) p.band = gemm_band() / CTAS;
+    const size_t stage_bytes = (size_t)(BM + BN / CTAS) * BK * 2;
     const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 2 + 3) & ~3) * 4;
     const size_t fixed = table + (size_t)BN * 12 + (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4 +
                          (2 * MAX_STAGES + 4 + 2 * TQ) * 8 + TQ * 4 + 16;
@@ -1123,14 +1255,15 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     }
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
-    auto kern = gemm_kernel<BN, EPI, NCHAIN>;
+    auto kern = gemm_kernel<BN, EPI, NCHAIN, CTAS>;
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // number of tiles
+    // number of tiles (of BM * CTAS rows)
     long long tiles = 0;
-    for (int mt = p.mt0; mt < p.mt1; mt += p.mt_step) tiles += p.n_tiles - (p.tri ? (mt * BM) / BN : 0);
+    for (int mt = p.mt0; mt < p.mt1; mt += p.mt_step) tiles += p.n_tiles - (p.tri ? (mt * BM * CTAS) / BN : 0);
     if (tiles <= p.tile_base) return 0;
-    int grid = sm_count();
+    int grid = sm_count() / CTAS;                  // one CTA (or CTA pair) per SM (TPC)
     if (tiles - p.tile_base < grid) grid = (int)(tiles - p.tile_base);
+    grid *= CTAS;
     // dynamic scheduler: one counter per launch out of a small rotating pool (launches on different
     // streams may overlap), zeroed on the launch stream
     static unsigned int* counters = nullptr;
@@ -1140,7 +1273,24 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     p.tile_counter = counters + (next_counter++ % N_COUNTERS);
     p.total_tiles = (int)tiles;
     MN_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), st));
-    kern<<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    if (CTAS == 1) {
+        kern<<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CTAS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
+    }
     MN_LAUNCH_CHECK();
     return 0;
 }
@@ -1206,14 +1356,16 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     if (check_planes("mn_corr_hist", d_hi, ldd, G)) return 1;
     MN_CHECK_ARG(inv_norm && hist && N >= 1 && row0 >= 0 && row1 <= N && row0 < row1, "mn_corr_hist: bad arguments");
     MN_CHECK_ARG(nbins >= 256 && nbins <= 32768 && (nbins & (nbins - 1)) == 0, "mn_corr_hist: nbins must be a power of two in [256, 32768]");
-    MN_CHECK_ARG((row0 % BM) == 0, "mn_corr_hist: row0 must be a multiple of %d", BM);
     MN_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "mn_corr_hist: bad shard");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.n_terms = corr_terms(p, d_lo != nullptr);
     p.tri = 1;
-    p.mt0 = (int)(row0 / BM) + shard_rank;
-    p.mt1 = (int)((row1 + BM - 1) / BM);
+    const bool wide = nbins <= 16384 && !getenv("MN_GEMM_BN128");
+    const int ctas = corr_ctas(wide), bm = BM * ctas;
+    MN_CHECK_ARG((row0 % bm) == 0, "mn_corr_hist: row0 must be a multiple of %d", bm);
+    p.mt0 = (int)(row0 / bm) + shard_rank;
+    p.mt1 = (int)((row1 + bm - 1) / bm);
     p.mt_step = shard_world;
     p.inv_a = inv_norm;
     p.inv_b = inv_norm;
@@ -1221,14 +1373,16 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.hist = reinterpret_cast<unsigned long long*>(hist);
     MN_CHECK_ARG(spill_tiles >= 0 && (spill_tiles == 0 || spill != nullptr), "mn_corr_hist: spill_tiles without a spill buffer");
     MN_CHECK_ARG((reinterpret_cast<uintptr_t>(spill) & 15) == 0, "mn_corr_hist: spill must be 16-byte aligned");
-    p.spill = spill_tiles > 0 ? spill : nullptr;
-    p.spill_tiles = (int)(spill_tiles > INT_MAX ? INT_MAX : spill_tiles);
+    p.spill_tiles = (int)(spill_tiles > INT_MAX ? INT_MAX : spill_tiles) & ~(ctas - 1);    // whole pairs only
+    p.spill = p.spill_tiles > 0 ? spill : nullptr;
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
     // rows beyond row1 inside the last tile belong to the next shard: mask them via M
     // 128 x 256 tiles move 25 % fewer operand bytes per flop through L2 (the measured bound); the table
     // must then leave room for >= 2 pipeline stages of 48 KB, i.e. nbins <= 16384
-    if (nbins <= 16384 && !getenv("MN_GEMM_BN128"))
+    if (wide && ctas == 2)
+        return launch_gemm<256, EPI_HIST, 1, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    if (wide)
         return launch_gemm<256, EPI_HIST, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     return launch_gemm<128, EPI_HIST, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
 }
@@ -1239,8 +1393,10 @@ int mn_corr_spill_layout(int64_t N, int64_t row0, int64_t row1, int32_t shard_ra
     MN_CHECK_ARG(n_tiles && tile_bytes && N >= 1 && row0 >= 0 && row1 <= N && row0 < row1 && (row0 % BM) == 0 &&
                      shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world,
                  "mn_corr_spill_layout: bad arguments");
-    const int bn = (nbins <= 16384 && !getenv("MN_GEMM_BN128")) ? 256 : 128;
-    *n_tiles = corr_tile_count(N, row0, row1, shard_rank, shard_world, bn);
+    const bool wide = nbins <= 16384 && !getenv("MN_GEMM_BN128");
+    const int bn = wide ? 256 : 128, ctas = corr_ctas(wide);
+    // stored tiles are 128 x bn; a CTA pair's 256-row tile counts as two
+    *n_tiles = corr_tile_count(N, row0, row1, shard_rank, shard_world, bn, BM * ctas) * ctas;
     *tile_bytes = (int64_t)BM * bn * 4;
     return 0;
 }
@@ -1262,7 +1418,6 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     MN_CHECK_ARG(inv_norm && lut && label && votes && degree && N >= 1 && L >= 1 && row0 >= 0 && row1 <= N && row0 < row1,
                  "mn_corr_vote: bad arguments");
     MN_CHECK_ARG(nbins >= 256 && nbins <= 32768 && (nbins & (nbins - 1)) == 0, "mn_corr_vote: nbins must be a power of two in [256, 32768]");
-    MN_CHECK_ARG((row0 % BM) == 0, "mn_corr_vote: row0 must be a multiple of %d", BM);
     MN_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world, "mn_corr_vote: bad shard");
     GemmParams p;
     memset(&p, 0, sizeof(p));
@@ -1271,8 +1426,11 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     // (MN_VOTE_FULL=1 computes all N^2 tiles instead; debugging aid)
     p.tri = getenv("MN_VOTE_FULL") ? 0 : 1;
     p.dbg_skip_col = getenv("MN_DBG_SKIP_COL") ? 1 : 0;
-    p.mt0 = (int)(row0 / BM) + shard_rank;
-    p.mt1 = (int)((row1 + BM - 1) / BM);
+    const bool wide = nbins <= 16384 && !getenv("MN_GEMM_BN128");
+    const int ctas = p.tri ? corr_ctas(wide) : 1, bm = BM * ctas;
+    MN_CHECK_ARG((row0 % bm) == 0, "mn_corr_vote: row0 must be a multiple of %d", bm);
+    p.mt0 = (int)(row0 / bm) + shard_rank;
+    p.mt1 = (int)((row1 + bm - 1) / bm);
     p.mt_step = shard_world;
     p.inv_a = inv_norm;
     p.inv_b = inv_norm;
@@ -1285,24 +1443,27 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     const __half* h = reinterpret_cast<const __half*>(d_hi);
     const __half* l = reinterpret_cast<const __half*>(d_lo);
     MN_CHECK_ARG(spill_tiles >= 0 && (spill_tiles == 0 || spill != nullptr), "mn_corr_vote: spill_tiles without a spill buffer");
-    const bool wide = nbins <= 16384 && !getenv("MN_GEMM_BN128");
     int rc = 0;
     // tiles [0, n_sp) of the linear tile order were spilled by pass 1: stream them from HBM;
     // the tensor cores recompute only the rest
-    const int64_t total = corr_tile_count(N, row0, row1, shard_rank, shard_world, wide ? 256 : 128);
+    const int64_t total = corr_tile_count(N, row0, row1, shard_rank, shard_world, wide ? 256 : 128, bm) * ctas;
     int64_t n_sp = (p.tri && spill) ? (spill_tiles < total ? spill_tiles : total) : 0;
+    n_sp &= ~(int64_t)(ctas - 1);                  // whole pairs only, as in pass 1
     if (n_sp > 0) {
         p.spill = const_cast<uint32_t*>(spill);
         p.spill_tiles = (int)n_sp;
         p.M = row1;
         p.N = N;
+        p.ctas = ctas;
         p.n_tiles = (int)((N + (wide ? 256 : 128) - 1) / (wide ? 256 : 128));
-        p.band = gemm_band();
+        p.band = gemm_band() / ctas;
         rc = wide ? launch_vote_spill<256>(p, (cudaStream_t)stream) : launch_vote_spill<128>(p, (cudaStream_t)stream);
         if (rc) return rc;
     }
-    p.tile_base = (int)n_sp;
-    if (wide)
+    p.tile_base = (int)(n_sp / ctas);
+    if (wide && ctas == 2)
+        rc = launch_gemm<256, EPI_VOTE, 1, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    else if (wide)
         rc = launch_gemm<256, EPI_VOTE, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     else
         rc = launch_gemm<128, EPI_VOTE, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
