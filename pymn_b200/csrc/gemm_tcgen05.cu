@@ -909,40 +909,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
 // ------------------------------------------------------------------ pass 2 from the rho spill
 // Streams the bin positions pass 1 left in HBM (tile-native layout, see EPI_HIST) instead of
-// recomputing the tiles on the tensor cores: an HBM-bound kernel, 4 B per cell pair.  Same VoteRows
-// arithmetic as the GEMM epilogue, hence bit-identical vote sums.
-// Every warp works on its own: it owns one 32-row quarter of `tb` consecutive tiles of the linear tile
-// order (same column tile, consecutive row tiles inside a band) and walks all 256 columns of each tile,
-// so that
+// recomputing the tiles on the tensor cores: 4 B per cell pair.  Same VoteRows arithmetic as the GEMM
+// epilogue, hence bit-identical vote sums.
+// Every warp works on its own: it owns one 32-row quarter of `tb` consecutive stored tiles (same column
+// tile, consecutive row tiles inside a band) and walks all 256 columns of each tile, so that
 //   - a row's running sum is flushed once per label run of the whole tile row (one 64-bit atomic per row
 //     and tile),
 //   - the column sums stay in registers across the run of tiles and are flushed when the column tile
 //     or the rows' label changes (one 64-bit reduction per column and ~tb tiles),
-//   - no barrier and no shared memory besides the LUT is needed.
-// The next 4 KB chunk is kept in flight in registers while the current one is processed.
-constexpr int SPILL_WARPS = 16;
+//   - no CTA barrier is needed.
+// Data path: each warp owns a 4 KB shared-memory slot; one lane fetches the warp's next chunk with a
+// bulk async copy (cp.async.bulk, mbarrier completion) as soon as the current one has been moved to
+// registers, so the HBM latency hides behind the ~600 instructions a chunk costs and no registers are
+// spent on prefetching: 24 warps per SM fit.  The kernel is bound by shared-memory lookups (one
+// random-bank LDS per pair, ~3.5-way conflicts) and latency, not by HBM.
+constexpr int SPILL_WARPS = 24;
+__device__ __forceinline__ void bulk_load_4k(void* smem_dst, const void* gsrc, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 4096;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 4096, [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(smem_u32(bar)) : "memory");
+}
 template <int BN>
 __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const GemmParams p, int tb) {
-    extern __shared__ __align__(16) uint32_t s_dyn[];
+    extern __shared__ __align__(128) unsigned char s_raw[];
     constexpr int HALF_COLS = BN / 2;
     constexpr int NCH = HALF_COLS / 32;         // chunks per column half
     constexpr int NCK = 2 * NCH;                // chunks per tile row
-    uint32_t* s_table = s_dyn;                  // [nbins + 2]
+    const int n_warps = (int)blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* s_slot = reinterpret_cast<uint4*>(s_raw) + (size_t)warp * 256;                    // this warp's 4 KB slot
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)n_warps * 4096) + warp;
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(s_raw + (size_t)n_warps * 4096 + (size_t)n_warps * 8);   // [nbins + 2]
     for (int i = threadIdx.x; i < p.nbins + 2; i += blockDim.x) s_table[i] = lut_pack(p.lut, i, p.nbins);
     const bool wide = p.lut[p.nbins + 1] != 0u;
+    if (lane == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int n_warps = (int)blockDim.x >> 5;
-    const int gw = blockIdx.x * n_warps + (threadIdx.x >> 5);
+    const int gw = blockIdx.x * n_warps + warp;
     const int quarter = gw & 3;                                  // rows quarter * 32 .. + 31 of every tile
     const int role0 = (quarter + 2) & 3;                         // GEMM epilogue warp (ew) that wrote them, column half 0
     const int n_blocks = (p.spill_tiles + tb - 1) / tb;
     const int blk_step = ((int)gridDim.x * n_warps) >> 2;
     const uint64_t pol_ef = l2_evict_first_policy();
     constexpr size_t TILE_V4 = (size_t)BM * BN / 4;
-    // uint4 index of (tile, chunk k of the tile row): role = role0 + 4 * (k / NCH), chunk-in-role = k % NCH
-    const uint4* base = reinterpret_cast<const uint4*>(p.spill) + lane;
+    // (tile, chunk k of the tile row): role = role0 + 4 * (k / NCH), chunk-in-role = k % NCH; 4 KB contiguous
+    const uint4* base = reinterpret_cast<const uint4*>(p.spill);
     auto chunk_src = [&](int tile, int k) {
         return base + (size_t)tile * TILE_V4 + (size_t)(((role0 + 4 * (k / NCH)) * NCH + (k % NCH)) * 256);
     };
@@ -950,13 +964,9 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
     TileIter it;
     it.init(p, BN, 0);
     int cur_tile = 0;
-    uint4 nx[8];
+    uint32_t phase = 0;
     int blk = gw >> 2;
-    if (blk < n_blocks) {
-        const uint4* src = chunk_src(blk * tb, 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) nx[k] = __ldcs(src + k * 32);
-    }
+    if (blk < n_blocks && lane == 0) bulk_load_4k(s_slot, chunk_src(blk * tb, 0), s_bar);
     // column side carried across tiles
     unsigned long long colacc[NCK];
 #pragma unroll
@@ -1004,37 +1014,52 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
                 col_n0 = n0;
                 col_lab = vr.lab_i;
             }
-#pragma unroll
+            // NOT unrolled: eight copies of the chunk body (~6,000 instructions each) overflow the instruction
+            // cache -- ncu showed "no instruction" as the top stall of the unrolled version.  lab_c / colacc
+            // stay in registers through compile-time indexed select / predicated-add chains.
+#pragma unroll 1
             for (int k = 0; k < NCK; ++k) {
                 uint32_t r[32];
+                mbar_wait(s_bar, phase);
+                phase ^= 1u;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    r[4 * j] = nx[j].x;
-                    r[4 * j + 1] = nx[j].y;
-                    r[4 * j + 2] = nx[j].z;
-                    r[4 * j + 3] = nx[j].w;
+                    const uint4 v = s_slot[j * 32 + lane];
+                    r[4 * j] = v.x;
+                    r[4 * j + 1] = v.y;
+                    r[4 * j + 2] = v.z;
+                    r[4 * j + 3] = v.w;
                 }
-                // this warp's next chunk: same tile, next tile of the block, or the first tile of its next block
+                __syncwarp();                     // every lane has taken its part of the slot
+                // refill the slot with this warp's next chunk: same tile, next tile of the run, or the first
+                // tile of its next run
                 int nt_tile = tile, nk = k + 1;
                 if (nk == NCK) {
                     nk = 0;
                     nt_tile = tile + 1;
                     if (nt_tile == t_end) nt_tile = (blk + blk_step < n_blocks) ? (blk + blk_step) * tb : -1;
                 }
-                if (nt_tile >= 0) {
-                    const uint4* src = chunk_src(nt_tile, nk);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) nx[j] = __ldcs(src + j * 32);
+                if (nt_tile >= 0 && lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before the async write
+                    bulk_load_4k(s_slot, chunk_src(nt_tile, nk), s_bar);
                 }
                 // label runs of this chunk's columns: a run starts where the label differs from the previous column's
-                int prev = __shfl_up_sync(0xffffffffu, lab_c[k], 1);
-                const int prev_chunk_last = __shfl_sync(0xffffffffu, lab_c[k > 0 ? k - 1 : 0], 31);
+                int lab_k = lab_c[0], lab_km1 = lab_c[0];
+#pragma unroll
+                for (int kk = 1; kk < NCK; ++kk) {
+                    lab_k = (kk == k) ? lab_c[kk] : lab_k;
+                    lab_km1 = (kk == k - 1) ? lab_c[kk] : lab_km1;
+                }
+                int prev = __shfl_up_sync(0xffffffffu, lab_k, 1);
+                const int prev_chunk_last = __shfl_sync(0xffffffffu, lab_km1, 31);
                 if (lane == 0) prev = prev_chunk_last;
-                const unsigned brk = __ballot_sync(0xffffffffu, (k == 0 && lane == 0) || prev != lab_c[k]);
-                const int lab_use = lab_c[k] < 0 ? 0 : lab_c[k];
+                const unsigned brk = __ballot_sync(0xffffffffu, (k == 0 && lane == 0) || prev != lab_k);
+                const int lab_use = lab_k < 0 ? 0 : lab_k;
                 const uint32_t mycol = vr.chunk(r, brk, LaneLabels{lab_use}, s_table, wide, true,
                                                 p.votes + (n0 + 32 * k) * (int64_t)p.L, p.L, pol_ef, lane);
-                colacc[k] += mycol;
+#pragma unroll
+                for (int kk = 0; kk < NCK; ++kk)
+                    if (kk == k) colacc[kk] += mycol;
             }
             vr.finish();
         }
@@ -1197,14 +1222,15 @@ static int corr_ctas(bool wide) { return (wide && !getenv("MN_GEMM_1CTA")) ? 2 :
 
 template <int BN>
 static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)((p.nbins + 2 + 3) & ~3) * 4;
-    auto kern = vote_spill_kernel<BN>;
-    MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int warps = SPILL_WARPS;
     if (const char* e = getenv("MN_SPILL_WARPS")) {    // experiment knob (multiple of 4)
         const int v = atoi(e);
         if (v >= 4 && v <= SPILL_WARPS && (v & 3) == 0) warps = v;
     }
+    // per warp a 4 KB slot + its mbarrier, then the packed LUT
+    const size_t smem = (size_t)warps * (4096 + 8) + (size_t)((p.nbins + 2 + 3) & ~3) * 4;
+    auto kern = vote_spill_kernel<BN>;
+    MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // tiles per run: the column sums are flushed about once per run, so long runs are cheaper (64 = one
     // column segment of a band), but every warp should still get >= 8 runs to balance the grid
     int tb = (int)(((long long)p.spill_tiles * 4) / (8ll * sm_count() * warps));
