@@ -32,8 +32,8 @@ def _keep_rows(n_pos):
 
 def metaNeighborUS_fast(X, S, C, node_degree_normalization, one_vs_best, compute_p):
     """MetaNeighborUS.py:228-306.  S, C: pandas Series (or arrays) of labels."""
-    S = np.asarray(S.values if hasattr(S, "values") else S, dtype=object)
-    C = np.asarray(C.values if hasattr(C, "values") else C, dtype=object)
+    S = S.values if hasattr(S, "values") else np.asarray(S)
+    C = C.values if hasattr(C, "values") else np.asarray(C)
     Xd = engine.to_device_matrix(prepare_matrix(X))     # the upload runs while the host encodes the labels
     lay = label_layout(S, C)
     r = engine.us_fast(Xd, lay, bool(node_degree_normalization), bool(one_vs_best))
@@ -78,9 +78,9 @@ def MetaNeighborUS_from_trained(trained_model, test_data, study_col, ct_col, nod
 def metaNeighborUS_default(adata, study_col, ct_col, node_degree_normalization, compute_p):
     """MetaNeighborUS.py:145-224: full cell x cell network.  Output is indexed
     [train label, test label] in globally sorted label order, like the reference."""
-    S = np.asarray(adata.obs[study_col].values, dtype=object)
-    C = np.asarray(adata.obs[ct_col].values, dtype=object)
-    Xd = engine.to_device_matrix(prepare_matrix(adata.X))     # the upload runs while the host encodes the labels
+    S = adata.obs[study_col].values         # numpy or pandas array; label_layout factorises either as it is
+    C = adata.obs[ct_col].values
+    Xd = engine.start_upload(prepare_matrix(adata.X))          # the upload runs while the host encodes the labels
     lay = label_layout(S, C)
     r = engine.us_default(Xd, lay, bool(node_degree_normalization))
     order = np.argsort(lay.sorted_pos)                       # row-order ids in globally sorted order

@@ -93,9 +93,33 @@ class RankedCells:
     rank2: torch.Tensor | None = None
 
 
+def alloc_ranked(M: int, G: int, dev) -> RankedCells:
+    """Uninitialised K1 outputs for M cells x G genes (filled by rank_normalize(..., out=, out_row0=))."""
+    ldd = (G + 63) // 64 * 64
+    return RankedCells(torch.empty((M, ldd), dtype=torch.float16, device=dev),
+                       torch.empty((M, ldd), dtype=torch.float16, device=dev) if G > 2048 else None, ldd,
+                       torch.empty((M,), dtype=torch.float32, device=dev),
+                       torch.empty((M,), dtype=torch.uint8, device=dev), M, G)
+
+
 def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
-                   want_xnorm=False, want_rank2=False) -> RankedCells:
-    """K1.  X: float32 CUDA [N, Gx] row-major, or a CsrMatrix."""
+                   want_xnorm=False, want_rank2=False, out: RankedCells = None, out_row0: int = 0) -> RankedCells:
+    """K1.  X: float32 CUDA [N, Gx] row-major, or a CsrMatrix.  With ``out`` the M = len(row_index) cells are
+    written into rows [out_row0, out_row0 + M) of preallocated outputs (the streamed pipeline ranks the
+    cells chunk by chunk as their rows arrive)."""
+    if out is not None:
+        assert row_index is not None and col_index is None and not want_xnorm and not want_rank2
+        M = int(row_index.numel())
+        r0, r1 = int(out_row0), int(out_row0) + M
+        if M > 0 and isinstance(X, CsrMatrix):
+            _lib.call("mn_rank_normalize_csr", X.indptr, X.indices, X.data, row_index, M, out.G, out.d_hi[r0:r1],
+                      out.d_lo[r0:r1] if out.d_lo is not None else None, out.ldd, out.inv_norm[r0:r1],
+                      out.flags[r0:r1], None, None, int(drop_mode))
+        elif M > 0:
+            _lib.call("mn_rank_normalize", X, int(X.stride(0)), row_index, None, M, out.G, out.d_hi[r0:r1],
+                      out.d_lo[r0:r1] if out.d_lo is not None else None, out.ldd, out.inv_norm[r0:r1],
+                      out.flags[r0:r1], None, None, int(drop_mode))
+        return out
     is_csr = isinstance(X, CsrMatrix)
     if is_csr:
         assert col_index is None, "column sub-setting of a CSR matrix is not supported"
@@ -300,6 +324,12 @@ def rho_spill_buffer(N: int, rank: int, world: int, nbins: int, dev, reserve_byt
     spill_tiles): as many tiles as fit into the free device memory minus ``reserve_bytes`` and a
     safety margin; the rest is recomputed.  ``MN_SPILL_GB`` caps the buffer (0 disables the spill)."""
     n_tiles, tile_bytes = _lib.corr_spill_layout(N, 0, N, rank, world, nbins)
+    return _spill_alloc(n_tiles, tile_bytes, dev, reserve_bytes, max_tiles)
+
+
+def _spill_alloc(n_tiles: int, tile_bytes: int, dev, reserve_bytes: int = 0, max_tiles=None):
+    """(cached uint8 buffer or None, granted tiles) for a spill of up to n_tiles tiles."""
+    total_tiles = n_tiles
     if max_tiles is not None:
         n_tiles = min(n_tiles, int(max_tiles))
     cap = _os.environ.get("MN_SPILL_GB")
@@ -313,7 +343,7 @@ def rho_spill_buffer(N: int, rank: int, world: int, nbins: int, dev, reserve_byt
     if cap is not None:
         budget = min(budget, int(float(cap) * (1 << 30)))
     want_tiles = max(0, min(n_tiles, budget // tile_bytes))
-    LAST_SPILL.update(total_tiles=_lib.corr_spill_layout(N, 0, N, rank, world, nbins)[0], tile_bytes=tile_bytes,
+    LAST_SPILL.update(total_tiles=total_tiles, tile_bytes=tile_bytes,
                       spill_tiles=int(want_tiles) if want_tiles >= (8 if max_tiles is None else 1) else 0)
     if want_tiles < (8 if max_tiles is None else 1):     # too small to pay for a second kernel
         return None, 0
@@ -437,13 +467,129 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
     return auc, n_pos, rc.flags, hist
 
 
+class AsyncUpload:
+    """A dense host matrix on its way to the device: row chunks copied LAST ROWS FIRST on a side stream,
+    one event per chunk.  ``chunks`` = [(row_lo, row_hi, event)] in upload order."""
+
+    def __init__(self, Xd, chunks, keep):
+        self.Xd, self.chunks, self._keep = Xd, chunks, keep
+        self.shape = tuple(Xd.shape)
+
+    def event_for_rows_from(self, row_lo: int):
+        """Event after which every input row >= row_lo is on the device."""
+        ev = self.chunks[-1][2]
+        for lo, _hi, e in self.chunks:
+            if lo <= row_lo:
+                ev = e
+                break
+        return ev
+
+    def wait_all(self):
+        torch.cuda.current_stream().wait_event(self.chunks[-1][2])
+        return self.Xd
+
+
+# Measured at config 2 (1.6 GB matrix, B200, PCIe Gen5): the plain upload already hides behind the host's
+# label encoding and the first kernels, and eight smaller launches per pass cost as much as the overlap
+# wins (e2e 123.6 ms plain vs 127.9 ms streamed), so the streamed path is opt-in (MN_STREAM_CHUNKS > 1).
+STREAM_MIN_BYTES = 64 << 20
+STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "1"))
+
+
+def start_upload(X):
+    """Begin moving the expression matrix to the device.  A large dense float32 matrix in PINNED host memory
+    is sent in row chunks, last rows first, on a side stream (AsyncUpload): the full-network pipeline
+    starts ranking and correlating the last cells while the first ones are still crossing PCIe
+    (us_default_streamed).  Anything else goes through to_device_matrix."""
+    if (STREAM_CHUNKS > 1 and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
+            and X.flags.c_contiguous and X.nbytes >= STREAM_MIN_BYTES):
+        t = torch.from_numpy(X)
+        if t.is_pinned():
+            dev = _dev()
+            N = int(X.shape[0])
+            Xd = torch.empty(tuple(X.shape), dtype=torch.float32, device=dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            bounds = [int(round(k * N / STREAM_CHUNKS)) for k in range(STREAM_CHUNKS + 1)]
+            chunks = []
+            with torch.cuda.stream(side):
+                for k in reversed(range(STREAM_CHUNKS)):
+                    lo, hi = bounds[k], bounds[k + 1]
+                    if hi > lo:
+                        Xd[lo:hi].copy_(t[lo:hi], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        chunks.append((lo, hi, ev))
+            Xd.record_stream(side)
+            return AsyncUpload(Xd, chunks, t)
+    return to_device_matrix(X)
+
+
+def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins=DEFAULT_NBINS, shard=None):
+    """The full-network pipeline overlapped with the upload.  The network passes cover the pairs i < j, so
+    the cells of device rows [b, b') only need rows >= b: processing the row chunks from the LAST to the
+    first, chunk k can be ranked (K1) and correlated (pass 1) as soon as the input rows of device rows
+    >= b_k have arrived -- with the usual study-sorted AnnData that is while earlier studies are still
+    in flight (an arbitrary cell order degenerates to upload-then-compute, never to a wrong result).
+    Integer histogram / vote sums make the result identical to us_default_device."""
+    rank, world, reduce_fn = shard if shard is not None else dist_shard()
+    dev = up.Xd.device
+    N, G = up.shape
+    cur = torch.cuda.current_stream()
+    perm_np = np.asarray(lay.perm)
+    perm, cell_label, seg_off = _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off)
+    nd = max(1, min(STREAM_CHUNKS, N // 4096))
+    bounds = sorted(set([0, N] + [min(N, int(round(k * N / nd / 256.0)) * 256) for k in range(1, nd)]))
+    nd = len(bounds) - 1
+    # lowest input row that device rows >= b need
+    suf_min = np.minimum.accumulate(perm_np[::-1])[::-1]
+    rc = alloc_ranked(N, G, dev)
+    layouts = [_lib.corr_spill_layout(N, bounds[k], bounds[k + 1], rank, world, nbins) for k in range(nd)]
+    tile_bytes = layouts[0][1]
+    spill, granted = _spill_alloc(sum(t for t, _ in layouts), tile_bytes, dev,
+                                  reserve_bytes=N * (L + 1) * 8 + N * L * 4 + (1 << 30))
+    hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
+    plan = []                                    # (row0, row1, spill slice or None, tiles) in processing order
+    off = 0
+    for k in reversed(range(nd)):
+        t_k = min(layouts[k][0], max(0, granted - off))
+        sl = spill[off * tile_bytes:] if (spill is not None and t_k > 0) else None
+        plan.append((bounds[k], bounds[k + 1], sl, t_k))
+        off += t_k
+    for r0, r1, sl, t_k in plan:
+        cur.wait_event(up.event_for_rows_from(int(suf_min[r0])))
+        rank_normalize(up.Xd, row_index=perm[r0:r1], drop_mode=0, out=rc, out_row0=r0)
+        _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, r0, r1, rank, world, G, nbins, hist,
+                  sl, t_k)
+    if reduce_fn is not None:
+        reduce_fn(hist)
+    lut = torch.empty((nbins + 2,), dtype=torch.int32, device=dev)
+    _lib.call("mn_corr_lut", hist, nbins, N, lut)
+    votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
+    degree = torch.zeros((N,), dtype=torch.int64, device=dev)
+    for r0, r1, sl, t_k in plan:
+        _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, r0, r1, rank, world, G, nbins, lut,
+                  cell_label, L, votes, degree, sl, t_k)
+    if reduce_fn is not None:
+        reduce_fn(votes)
+        reduce_fn(degree)
+    vmat = torch.empty((L, N), dtype=torch.float32, device=dev)
+    _lib.call("mn_votes_finalize", votes, degree, cell_label, N, L, int(bool(ndn)), vmat, N)
+    auc, n_pos = auroc(vmat, L, None, None, seg_off, S, cell_label, L)
+    return auc, n_pos, rc.flags, hist
+
+
 def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):
     """metaNeighborUS_default.  Returns dict(auroc [L, L] rows = TEST labels, cols = TRAIN
-    labels, both in row order -- the caller transposes / reorders, MetaNeighborUS.py:213)."""
-    Xd = to_device_matrix(X)
+    labels, both in row order -- the caller transposes / reorders, MetaNeighborUS.py:213).
+    X: host / device matrix, CsrMatrix, or an AsyncUpload from start_upload()."""
     L, S = len(lay.row_labels), len(lay.studies)
-    auc, n_pos, flags, hist = us_default_device(Xd, _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off), L, S,
-                                                ndn, nbins)
+    if isinstance(X, AsyncUpload):
+        auc, n_pos, flags, hist = us_default_streamed(X, lay, L, S, ndn, nbins)
+    else:
+        Xd = to_device_matrix(X)
+        auc, n_pos, flags, hist = us_default_device(Xd, _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off),
+                                                    L, S, ndn, nbins)
     return dict(auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(), flags=flags.cpu().numpy(),
                 hist_total=int(hist.sum().item()))
 

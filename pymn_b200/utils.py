@@ -26,13 +26,22 @@ def join_labels(x, y, replace_bar=False):
 
 def _factorize_sorted(vec):
     """Sorted unique values (Python / code-point order, as np.unique on object
-    or str arrays) and int64 codes."""
+    or str arrays) and int64 codes.  ``vec``: numpy array, pandas Series or pandas array -- a pandas
+    string column is factorised as it is (Arrow dictionary encoding), without a detour through
+    200,000 Python objects."""
     import pandas as pd
-    vec = np.asarray(vec)
+    if isinstance(vec, pd.Series):
+        vec = vec.values
+    if not isinstance(vec, np.ndarray) and getattr(getattr(vec, "dtype", None), "name", "") == "category":
+        vec = np.asarray(vec, dtype=object)
     # hash-factorise the N cells (O(N)), then sort only the handful of distinct values
     codes, uniq = pd.factorize(vec, sort=False)
-    uniq = np.asarray(uniq)
-    if vec.dtype.kind in "OUS":
+    if (codes < 0).any():                      # missing values: the reference would stringify them ("nan")
+        vec = np.array([str(v) for v in np.asarray(vec, dtype=object)], dtype=object)
+        codes, uniq = pd.factorize(vec, sort=False)
+    kind = np.asarray(vec[:1]).dtype.kind if len(vec) else "O"
+    uniq = np.asarray(uniq, dtype=object) if kind in "OUST" else np.asarray(uniq)
+    if kind in "OUST":
         names = [v if isinstance(v, str) else str(v) for v in uniq.tolist()]
         order = sorted(range(len(names)), key=lambda i: names[i])          # code-point order, as np.unique
     else:
@@ -40,7 +49,14 @@ def _factorize_sorted(vec):
         names = [str(v) for v in uniq.tolist()]
     remap = np.empty(len(order), np.int64)
     remap[np.asarray(order, dtype=np.int64)] = np.arange(len(order))
-    return np.array([names[i] for i in order], dtype=object), remap[codes]
+    return np.array([names[i] for i in order], dtype=object), remap[np.asarray(codes, dtype=np.int64)]
+
+
+def _stable_argsort_small(codes: np.ndarray, n_values: int) -> np.ndarray:
+    """Stable argsort of non-negative integer codes < n_values; 16-bit keys take NumPy's O(N) radix sort."""
+    if n_values <= 32767:
+        return np.argsort(codes.astype(np.int16), kind="stable")
+    return np.argsort(codes, kind="stable")
 
 
 @dataclass
@@ -76,7 +92,14 @@ def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     ct_uniq, ct_codes = _factorize_sorted(ctype)
     n_ct = len(ct_uniq)
     pair = st_codes * n_ct + ct_codes
-    pair_uniq, pair_codes = np.unique(pair, return_inverse=True)
+    # distinct (study, type) pairs, ascending, and each cell's index into them (O(N): the code space is small)
+    n_codes = len(st_uniq) * n_ct
+    if n_codes <= max(4 * len(pair), 1 << 20):
+        present = np.bincount(pair, minlength=n_codes) > 0
+        pair_uniq = np.flatnonzero(present)
+        pair_codes = (np.cumsum(present) - 1)[pair]
+    else:
+        pair_uniq, pair_codes = np.unique(pair, return_inverse=True)
     st_of = pair_uniq // n_ct
     st_names = [s.replace("|", ".") for s in st_uniq.tolist()] if replace_bar else st_uniq.tolist()
     if replace_bar:
@@ -89,7 +112,7 @@ def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     rank_of_pair = np.empty(len(names), np.int64)
     rank_of_pair[order] = np.arange(len(names))
     cell_label = rank_of_pair[pair_codes]
-    perm = np.argsort(cell_label, kind="stable")
+    perm = _stable_argsort_small(cell_label, len(names))
     row_labels = names[order]
     label_study = st_of[order].astype(np.int32)
     n_lab = len(names)
@@ -116,7 +139,7 @@ def joint_layout(study, ctype):
     ct_uniq, ct_codes = _factorize_sorted(ctype)
     S, K = len(st_uniq), len(ct_uniq)
     joint = st_codes * K + ct_codes
-    perm = np.argsort(joint, kind="stable")
+    perm = _stable_argsort_small(joint, S * K)
     counts = np.bincount(joint, minlength=S * K)
     lab_row_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     seg_lab_off = (np.arange(S + 1) * K).astype(np.int32)

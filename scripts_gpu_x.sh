@@ -1,16 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() { name=$1; shift; echo "=== $name"; timeout 600 "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?"; tail -${TAILN:-3} gpurun_out/$name.log | cut -c1-400; }
-summ() { python - "$1" <<'PY'
-import json,sys
-l=[x for x in open(f'gpurun_out/{sys.argv[1]}.log') if x.startswith('{')]
-if l:
-    d=json.loads(l[-1]); print(sys.argv[1], round(d['ms_per_step'],2), {k:round(v,2) for k,v in d['stage_ms'].items()}, 'e2e', round(d['e2e']['ms_per_step'],1), d['clocks']['sm_mhz'])
-PY
-}
-TAILN=15 run t_corr python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k corr
-grep -q passed gpurun_out/t_corr.log || exit 1
-MN_SPILL_TB=2 TAILN=6 run t_corr2 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_e2e.py -q -m gpu -x
-for w in 24 16; do
-MN_SPILL_WARPS=$w run b_w$w python bench.py --steps 3 --warmup 3 --no-cpu-baseline >/dev/null; summ b_w$w
+for ch in 8 1 4 1 8; do
+echo "== chunks $ch"; MN_STREAM_CHUNKS=$ch timeout 600 python tools/profile_e2e.py 2>&1 | grep -E "e2e calls|us_default|label_layout|cpu'|MetaNeighborUS.py" | head -12
 done

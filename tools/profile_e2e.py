@@ -44,8 +44,11 @@ def call():
 
 for _ in range(2):
     call()
-t0 = time.perf_counter()
-call()
-print(f"e2e call: {(time.perf_counter() - t0) * 1e3:.1f} ms")
+ts = []
+for _ in range(8):
+    t0 = time.perf_counter()
+    call()
+    ts.append((time.perf_counter() - t0) * 1e3)
+print("e2e calls (ms):", " ".join(f"{t:.1f}" for t in ts), f"| median {np.median(ts):.1f}")
 cProfile.run("call()", "/tmp/e2e.prof")
 pstats.Stats("/tmp/e2e.prof").sort_stats("cumtime").print_stats(22)
