@@ -47,6 +47,7 @@ struct GemmParams {
     int64_t M;        // rows of A
     int64_t N;        // rows of B
     int k_blocks;     // ceil(G / 64)
+    int k_last;       // MMA steps (of 16 genes) the last k-block needs: ceil((G - 64 (k_blocks - 1)) / 16)
     int n_terms;      // plane products accumulated into one tile
     int a_sel[MAX_TERMS];   // 0 = hi plane, 1 = lo plane
     int b_sel[MAX_TERMS];
@@ -680,6 +681,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (tile < 0) break;
                 mbar_wait(&tempty_bar[a], aph ^ 1u);
                 tc_fence_after();
+                int kb = 0;
                 for (int i = 0; i < n_iters; ++i) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC_COLS + (i % NCHAIN) * BN);
                     mbar_wait(&full_bar[s], ph);
@@ -687,8 +689,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     const uint32_t sa = smem_u32(ring + (size_t)s * STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                    // the last k-block of a plane product holds G mod 64 genes (the rest is zero padding):
+                    // only the 16-gene steps that carry data are issued (G = 2000: 1 of 4)
+                    const int k_steps = (kb == p.k_blocks - 1) ? p.k_last : BK / UMMA_K;
+                    if (++kb == p.k_blocks) kb = 0;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (k >= k_steps) break;
                         // advance the start address by k * 16 elements * 2 B = 32 B = 2 (16-byte units)
                         if constexpr (PAIR)
                             tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
@@ -803,24 +810,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
+                    // column scales four at a time (one broadcast LDS.128 instead of four LDS: the epilogue's
+                    // shared-memory wavefronts compete with the TMA writes and the MMA operand reads)
+                    const float4* invb4 = reinterpret_cast<const float4*>(s_invb + c0);
                     if (row_live) {
                         if (!diag_tile) {
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const float inv_j = s_invb[c0 + c];
-                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins, q_top);
-                                const bool use = inv_j > 0.f;
-                                atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
-                                r[c] = use ? qv : 0u;
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 ib = invb4[c4];
+                                const float ibv[4] = {ib.x, ib.y, ib.z, ib.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int c = 4 * c4 + u;
+                                    const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], half_bins, q_top);
+                                    const bool use = ibv[u] > 0.f;
+                                    atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
+                                    r[c] = use ? qv : 0u;
+                                }
                             }
                         } else {
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const float inv_j = s_invb[c0 + c];
-                                const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, inv_j, half_bins, q_top);
-                                const bool use = inv_j > 0.f && (n0 + c0 + c > m);
-                                atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
-                                r[c] = use ? qv : 0u;
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 ib = invb4[c4];
+                                const float ibv[4] = {ib.x, ib.y, ib.z, ib.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int c = 4 * c4 + u;
+                                    const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], half_bins, q_top);
+                                    const bool use = ibv[u] > 0.f && (n0 + c0 + c > m);
+                                    atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
+                                    r[c] = use ? qv : 0u;
+                                }
                             }
                         }
                     } else if (do_spill) {
@@ -852,10 +872,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_chains<BN, NCHAIN>(t_base + (uint32_t)c0, n_chains, r);
+                    const float4* invb4 = reinterpret_cast<const float4*>(s_invb + c0);
                     if (!diag_tile) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            r[c] = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins, q_top);
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 ib = invb4[c4];
+                            r[4 * c4] = rho_q(__uint_as_float(r[4 * c4]), inv_i_half, ib.x, half_bins, q_top);
+                            r[4 * c4 + 1] = rho_q(__uint_as_float(r[4 * c4 + 1]), inv_i_half, ib.y, half_bins, q_top);
+                            r[4 * c4 + 2] = rho_q(__uint_as_float(r[4 * c4 + 2]), inv_i_half, ib.z, half_bins, q_top);
+                            r[4 * c4 + 3] = rho_q(__uint_as_float(r[4 * c4 + 3]), inv_i_half, ib.w, half_bins, q_top);
+                        }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
@@ -1262,6 +1288,7 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     p.N = N;
     p.ctas = CTAS;
     p.k_blocks = (G + BK - 1) / BK;
+    p.k_last = (G - (p.k_blocks - 1) * BK + UMMA_K - 1) / UMMA_K;
     p.n_tiles = (int)((N + BN - 1) / BN);
     if (p.band <= 0) p.band = gemm_band() / CTAS;
     const size_t stage_bytes = (size_t)(BM + BN / CTAS) * BK * 2;

@@ -16,6 +16,7 @@ timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2.csv \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_c2.log 2>&1
 echo "rc=$?"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|rank_count_kernel|auroc_kernel" -s 12 -c 4 -o gpurun_out/prof_r01_c2 -f \
-   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_c2.log 2>&1
+timeout 600 python bench.py --config c2_mid --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain_mid.log 2>&1 && \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|rank_count_kernel|auroc_kernel|vote_spill" -s 15 -c 5 -o gpurun_out/prof_r01_mid -f \
+   python bench.py --config c2_mid --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_mid.log 2>&1
 echo "rc=$?"
