@@ -76,6 +76,18 @@ int mn_rank_normalize_csr(const int64_t* indptr, const int32_t* indices, const f
                           int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
                           int32_t drop_mode, mn_stream_t stream);
 
+/* ---- gene statistics for variableGenes (the step before the hot path) -------------
+ * Replaces bottleneck.median(adata.X, axis=0) and np.var(adata.X, axis=0) over the cells of each
+ * study (variableGenes.py:22-27, called per study at :69-72).
+ *   X          [*, ldx] float32 row-major cells x genes (finite values)
+ *   row_index  int32[M] or NULL: position i of the study-sorted order is input row row_index[i]
+ *   seg_off    int32[n_seg+1]: study t owns positions [seg_off[t], seg_off[t+1])
+ *   median     float64 [n_seg, G]: per-gene median (mean of the two middle order statistics; exact)
+ *   variance   float64 [n_seg, G]: per-gene population variance (ddof = 0), accumulated in float64
+ * An empty study yields NaN.  4-pass radix select: HBM-bound, 4 x 4 B per element. */
+int mn_gene_stats(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* seg_off,
+                  int32_t n_seg, int32_t G, double* median, double* variance, mn_stream_t stream);
+
 /* ---- K2: cluster centroids ----------------------------------------------
  * Replaces X_norm @ onehot (MetaNeighborUS.py:284, trainModel.py:43,
  * MetaNeighbor.py:170 inner product) and n_cells_per_cluster (:288).

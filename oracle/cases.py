@@ -52,6 +52,10 @@ CASES = {
                         n_sets=8, set_lo=8, set_hi=60, all_hvg=True, drop_type=[2, 1]),
     "mn_fast_nondn": dict(kind="supervised", seed=44, ndn=False, fast=True, S=3, n=120, G=200, K=5,
                           n_sets=5, set_lo=8, set_hi=60, all_hvg=True),
+    # variableGenes (variableGenes.py) -- counts, and log-normalised floats (float64 X: the reference then
+    # computes np.var in float64 like the kernel does)
+    "var_genes_counts": dict(kind="var_genes", seed=51, S=3, n=301, G=400, K=5),
+    "var_genes_log1p": dict(kind="var_genes", seed=52, S=2, n=250, G=320, K=4, log1p=True),
 }
 
 

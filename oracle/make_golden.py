@@ -81,6 +81,12 @@ def run_reference(name, spec):
                 one_vs_best=spec.get("ovb", False), symmetric_output=False, save_uns=False)
             out.update({f"auroc_{k}": v for k, v in _table(res).items()})
             out.update({f"model_{k}": v for k, v in _table(model).items()})
+        elif kind == "var_genes":
+            ad = _adata(inp)
+            ad.X = inp["X"].astype(np.float64)
+            res = ref.variableGenes.variableGenes(ad, "study_id", return_vect=True)
+            out["selected"] = np.asarray(res.values, bool)
+            out["genes"] = np.asarray([str(v) for v in res.index], dtype=str)
         elif kind == "supervised":
             ad = _adata(inp)
             gs = pd.DataFrame(inp["genesets"], index=pd.Index(inp["gs_genes"].astype(object), dtype=object),

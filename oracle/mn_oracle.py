@@ -463,3 +463,33 @@ class _quiet:
 
     def __exit__(self, *a):
         return self._cm.__exit__(*a)
+
+
+# ---------------------------------------------------------------------------
+# variableGenes (reference pymn/variableGenes.py:7-77) -- SURVEY section 8f-2
+# ---------------------------------------------------------------------------
+def compute_var_genes(x: np.ndarray) -> np.ndarray:
+    """variableGenes.py:22-37 for one dataset (cells x genes): per-gene median and population variance,
+    median deciles (midpoint quantiles, right-closed digitize), variance quartiles inside each decile,
+    keep the top quartile.  float64 throughout."""
+    x = np.asarray(x, np.float64)
+    median = np.median(x, axis=0)
+    variance = np.var(x, axis=0)
+    bins = np.quantile(median, q=np.linspace(0, 1, 11), method="midpoint")
+    digits = np.digitize(median, bins, right=True)
+    selected = np.zeros(x.shape[1], bool)
+    for i in np.unique(digits):
+        filt = digits == i
+        var_tmp = variance[filt]
+        bins_tmp = np.nanquantile(var_tmp, q=np.linspace(0, 1, 5))
+        selected[filt] = np.digitize(var_tmp, bins_tmp) >= 4
+    return selected
+
+
+def variable_genes(x: np.ndarray, study) -> np.ndarray:
+    """variableGenes.py:62-73: a gene must be selected in every study."""
+    study = np.asarray(study, dtype=object)
+    out = np.ones(np.asarray(x).shape[1], bool)
+    for st in np.unique(study):
+        out &= compute_var_genes(np.asarray(x)[study == st])
+    return out

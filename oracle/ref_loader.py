@@ -14,7 +14,7 @@ network.  The recipe: register a synthetic ``pymn``
 package, shim ``bottleneck``'s five functions with their SciPy / NumPy
 equivalents (average-tie, 1-based, float64 -- the documented semantics of
 ``bottleneck.rankdata`` / ``nanrankdata``), and exec
-``pymn/{utils,MetaNeighborUS,MetaNeighbor,trainModel}.py`` as they lie.
+``pymn/{utils,MetaNeighborUS,MetaNeighbor,trainModel,variableGenes}.py`` as they lie.
 """
 from __future__ import annotations
 
@@ -59,7 +59,7 @@ _loaded = None
 
 def load_reference():
     """Returns a namespace with the reference modules: .utils, .MetaNeighborUS,
-    .MetaNeighbor, .trainModel (module objects)."""
+    .MetaNeighbor, .trainModel, .variableGenes (module objects)."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -79,7 +79,7 @@ def load_reference():
     ns = types.SimpleNamespace()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")          # SyntaxWarning: `is not "highly_variable"` (trainModel.py:29)
-        for name in ("utils", "MetaNeighborUS", "MetaNeighbor", "trainModel"):
+        for name in ("utils", "MetaNeighborUS", "MetaNeighbor", "trainModel", "variableGenes"):
             path = os.path.join(REFERENCE_ROOT, "pymn", f"{name}.py")
             spec = importlib.util.spec_from_file_location(f"pymn.{name}", path)
             mod = importlib.util.module_from_spec(spec)

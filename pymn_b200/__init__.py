@@ -1,9 +1,9 @@
 """pymn_b200 -- B200-native MetaNeighbor scoring hot path behind pyMN's API.
 
-Drop-in for the three hot-path entry points of gillislab/pyMN
-(reference pymn/__init__.py:2-4,18):
+Drop-in for the hot-path entry points of gillislab/pyMN and the step right before them
+(reference pymn/__init__.py:2-5,18):
 
-    from pymn_b200 import MetaNeighborUS, MetaNeighbor, trainModel, join_labels
+    from pymn_b200 import MetaNeighborUS, MetaNeighbor, trainModel, variableGenes, join_labels
 
 Importing the package does not need a GPU; calling any entry point does, and
 raises if the CUDA library (``libpymn_b200.so``) or a CUDA device is missing --
@@ -12,8 +12,10 @@ there is no CPU fallback.
 from .MetaNeighbor import MetaNeighbor
 from .MetaNeighborUS import MetaNeighborUS
 from .trainModel import trainModel
+from .variableGenes import variableGenes
 from .utils import join_labels
 from .anndata_lite import AnnDataLite
+from .model_io import load_model, save_model
 
-__all__ = ["MetaNeighborUS", "MetaNeighbor", "trainModel", "join_labels", "AnnDataLite"]
+__all__ = ["MetaNeighborUS", "MetaNeighbor", "trainModel", "variableGenes", "join_labels", "AnnDataLite", "save_model", "load_model"]
 __version__ = "0.1.0"

@@ -145,6 +145,18 @@ def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
     return RankedCells(d_hi, d_lo, ldd, inv_norm, flags, M, G, xnorm, rank2)
 
 
+def gene_stats(X, perm: np.ndarray, seg_off: np.ndarray):
+    """Per-study per-gene median and variance (variableGenes.py:22-27).  X: dense host / device matrix
+    [N, G]; perm int32[N] sorts the cells by study, seg_off int32[S+1] are the study ranges of that order.
+    Returns (median float64 [S, G], variance float64 [S, G]) on the host."""
+    Xd = to_device(X, torch.float32)
+    S, G = int(len(seg_off) - 1), int(Xd.shape[1])
+    med = torch.empty((S, G), dtype=torch.float64, device=Xd.device)
+    var = torch.empty((S, G), dtype=torch.float64, device=Xd.device)
+    _lib.call("mn_gene_stats", Xd, int(Xd.stride(0)), _i32(perm), _i32(seg_off), S, G, med, var)
+    return med.cpu().numpy(), var.cpu().numpy()
+
+
 def centroids(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: int = 0):
     """K2.  Returns (C float32 [L + extra_rows, ldd] (extra rows zero), n_valid float32 [L + extra_rows])."""
     C = torch.zeros((L + extra_rows, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)

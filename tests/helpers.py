@@ -75,6 +75,9 @@ def oracle_run(spec, inp, train_inp=None):
         r = O.metaneighbor_us_from_trained(aligned, mcols, np.asarray(inp["X"], np.float32)[:, sel], s, c,
                                            spec["ndn"], spec.get("ovb", False))
         out.update(auroc_values=r[0], auroc_rows=r[1], auroc_cols=r[2])
+    elif kind == "var_genes":
+        out["selected"] = O.variable_genes(np.asarray(inp["X"], np.float32), s)
+        out["genes"] = np.asarray(inp["genes"], dtype=object)
     elif kind == "supervised":
         gs = inp["genesets"]
         names = np.array([f"set{j}" for j in range(gs.shape[1])], dtype=object)

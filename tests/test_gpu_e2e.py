@@ -197,3 +197,71 @@ def test_default_path_streamed_upload_identical(shuffle, monkeypatch):
     got = engine.us_default(up, lay, True)
     assert np.array_equal(got["auroc"], ref["auroc"]) and np.array_equal(got["n_pos"], ref["n_pos"])
     assert got["hist_total"] == ref["hist_total"] and np.array_equal(got["flags"], ref["flags"])
+
+
+# ---- variableGenes -----------------------------------------------------------
+@pytest.mark.parametrize("name", C.list_cases("var_genes"))
+def test_golden_variable_genes(name):
+    """The boolean gene vector equals the unmodified reference's, gene for gene."""
+    import pymn_b200
+    spec, inp, ref = C.load_case(name)
+    ad = make_adata(inp)
+    got = pymn_b200.variableGenes(ad, "study_id", return_vect=True)
+    assert [str(g) for g in got.index] == [str(g) for g in ref["genes"]]
+    assert np.array_equal(np.asarray(got.values, bool), ref["selected"])
+    assert pymn_b200.variableGenes(ad, "study_id") is None
+    assert np.array_equal(np.asarray(ad.var["highly_variable"].values, bool), ref["selected"])
+
+
+def test_gene_stats_kernel_exact():
+    """mn_gene_stats: medians are exact order statistics (odd and even study sizes, negatives, ties,
+    a gene count that is not a multiple of 32), variances match float64 NumPy to rounding."""
+    from pymn_b200 import engine
+    rng = np.random.default_rng(3)
+    n, g = 4097, 77
+    x = rng.poisson(0.7, size=(n, g)).astype(np.float32)
+    x[:, 5] = rng.normal(size=n).astype(np.float32)            # floats incl. negatives
+    x[:, 6] = -x[:, 6]
+    x[:, 7] = 3.0                                              # constant gene
+    seg = np.array([0, 1000, 1001, 1001, 4097], dtype=np.int32)     # even, single-cell, EMPTY, odd studies
+    perm = rng.permutation(n).astype(np.int32)
+    med, var = engine.gene_stats(x, perm, seg)
+    xs = x[perm].astype(np.float64)
+    for k in range(4):
+        blk = xs[seg[k]:seg[k + 1]]
+        if blk.shape[0] == 0:
+            assert np.isnan(med[k]).all() and np.isnan(var[k]).all()
+            continue
+        assert np.array_equal(med[k], np.median(blk, axis=0)), f"median, study {k}"
+        assert np.allclose(var[k], np.var(blk, axis=0), rtol=1e-12, atol=1e-12), f"variance, study {k}"
+
+
+def test_variable_genes_config_size_matches_oracle():
+    """20,000 cells x 2,000 genes, 2 studies: same genes as the NumPy restatement."""
+    import pymn_b200
+    x, s, c = make_counts(5, 2, 10000, 2000, 20)
+    genes = np.array([f"g{i}" for i in range(x.shape[1])], dtype=object)
+    ad = make_adata(dict(X=x, study=s, ctype=c, genes=genes, hvg=np.ones(x.shape[1], bool)))
+    got = pymn_b200.variableGenes(ad, "study_id", return_vect=True)
+    ref = O.variable_genes(x, s)
+    assert np.array_equal(np.asarray(got.values, bool), ref)
+
+
+def test_pretrained_model_through_csv(tmp_path):
+    """trainModel -> save_model -> load_model -> MetaNeighborUS(trained_model=...) gives the
+    table of the in-memory model, bit for bit (the protocol-2 round trip)."""
+    import pymn_b200
+    spec, inp, ref = C.load_case("pretrained_ndn")
+    train_inp = C.build_inputs(spec["train"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = pymn_b200.trainModel(make_adata(train_inp), "study_id", "cell_type")
+        pymn_b200.save_model(model, tmp_path / "m.csv")
+        loaded = pymn_b200.load_model(tmp_path / "m.csv")
+        assert np.array_equal(loaded.values, model.values) and list(loaded.columns) == list(model.columns)
+        kw = dict(node_degree_normalization=True, symmetric_output=False, save_uns=False)
+        a = pymn_b200.MetaNeighborUS(make_adata(inp), "study_id", "cell_type", trained_model=model, **kw)
+        b = pymn_b200.MetaNeighborUS(make_adata(inp), "study_id", "cell_type", trained_model=loaded, **kw)
+    assert np.array_equal(a.values, b.values, equal_nan=True) and list(a.index) == list(b.index)
+    assert_table_close(b.values, b.index, b.columns, ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"],
+                       _tol(inp), "pretrained via csv")

@@ -108,3 +108,30 @@ def test_shard_and_gather_single_rank():
     assert list(shard_columns(7, 1, 3)) == [1, 4]
     a = np.arange(6.0).reshape(2, 3)
     assert gather_columns(a, 3, 0, 1) is a
+
+
+def test_model_csv_round_trip(tmp_path):
+    """the (1 + G) x L model table survives to_csv / read_csv(index_col=0) bit for bit,
+    a file written R-style (quoted header, empty corner cell) loads too, and bad files fail early."""
+    import pandas as pd
+    import pymn_b200
+    rng = np.random.default_rng(0)
+    genes = [f"g{i}" for i in range(25)]
+    cols = ["s1|a", "s1|b c", "s10|a"]
+    vals = np.vstack([[12, 7, 30], rng.normal(size=(25, 3))])
+    model = pd.DataFrame(vals, index=["n_cells"] + genes, columns=cols)
+    path = tmp_path / "model.csv"
+    pymn_b200.save_model(model, path)
+    back = pymn_b200.load_model(path)
+    assert list(back.index) == list(model.index) and list(back.columns) == cols
+    assert np.array_equal(back.values, model.values)
+    r_path = tmp_path / "model_r.csv"
+    with open(r_path, "w") as f:
+        f.write('"",' + ",".join(f'"{c}"' for c in cols) + "\n")
+        for name, row in zip(model.index, model.values):
+            f.write(f'"{name}",' + ",".join(repr(float(v)) for v in row) + "\n")
+    assert np.array_equal(pymn_b200.load_model(r_path).values, model.values)
+    bad = model.copy()
+    bad.index = ["cells"] + genes
+    with pytest.raises(AssertionError):
+        pymn_b200.save_model(bad, tmp_path / "bad.csv")

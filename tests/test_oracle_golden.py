@@ -83,3 +83,13 @@ def test_auroc_cells_match_sklearn():
     for c in range(3):
         for l in range(4):
             assert abs(roc[c, l] - roc_auc_score(codes == c, votes[:, l])) < 1e-12
+
+
+@pytest.mark.parametrize("name", C.list_cases("var_genes"))
+def test_variable_genes(name):
+    """variableGenes: the boolean gene vector is an index-type result -- exact."""
+    spec, inp, ref = C.load_case(name)
+    got = oracle_run(spec, inp)
+    assert [str(g) for g in got["genes"]] == [str(g) for g in ref["genes"]]
+    assert np.array_equal(got["selected"], ref["selected"]), name
+    assert 0 < ref["selected"].sum() < ref["selected"].size
