@@ -9,13 +9,16 @@
 // still share the prefix of the wanted order statistic -- into a [256 bins][32 genes] shared-memory
 // table, so lane g only ever touches bank g: no bank conflicts, and only warps collide on an address.
 // Two order statistics are tracked (ranks (n-1)/2 and n/2; their mean is the median), each with its own
-// table.  The first sweep also accumulates sum and sum of squares in float64 for the variance
-// (population variance, ddof = 0, as np.var).  HBM-bound: 4 sweeps x 4 B per element.
+// table.  Expression columns are runs of equal values (mostly zeros), so every lane keeps a (digit, count)
+// run in registers and only touches the table when the digit changes.  The first sweep also
+// accumulates sum and sum of squares in float64 for the variance (population variance, ddof = 0, as
+// np.var).  HBM-bound by design: 4 sweeps x 4 B per element.
 #include "common.cuh"
 
 namespace mn {
 
-constexpr int GS_WARPS = 8;
+constexpr int GS_WARPS = 16;
+constexpr int GS_UNROLL = 8;          // row loads in flight per lane
 constexpr int GS_THREADS = GS_WARPS * 32;
 
 __device__ __forceinline__ float key_to_float(uint32_t k) {
@@ -59,12 +62,13 @@ gene_stats_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
         __syncthreads();
         const uint32_t pre0 = s_prefix[lane], pre1 = s_prefix[32 + lane];
         const bool same = (pre0 == pre1);
-        // rows of the study, GS_WARPS apart, four loads in flight per lane
-        for (int rb = r0 + warp; rb < r1; rb += GS_WARPS * 4) {
-            float v[4];
-            bool ok[4];
+        // rows of the study, GS_WARPS apart, GS_UNROLL loads in flight per lane
+        uint32_t run_d0 = 0xffffffffu, run_c0 = 0u, run_d1 = 0xffffffffu, run_c1 = 0u;
+        for (int rb = r0 + warp; rb < r1; rb += GS_WARPS * GS_UNROLL) {
+            float v[GS_UNROLL];
+            bool ok[GS_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GS_UNROLL; ++u) {
                 const int r = rb + u * GS_WARPS;
                 ok[u] = live && r < r1;
                 v[u] = 0.f;
@@ -74,21 +78,37 @@ gene_stats_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GS_UNROLL; ++u) {
                 if (!ok[u]) continue;
                 const uint32_t k = float_key(v[u]);
                 if (pass == 0) {
                     sum += (double)v[u];
                     sq += (double)v[u] * (double)v[u];
-                    atomicAdd(&hist[(k >> 24) * 32 + lane], 1u);
-                } else {
-                    const uint32_t hi = k >> (shift + 8);
-                    const uint32_t d = (k >> shift) & 0xffu;
-                    if (hi == pre0) atomicAdd(&hist[d * 32 + lane], 1u);
-                    if (!same && hi == pre1) atomicAdd(&hist[(256 + d) * 32 + lane], 1u);
+                }
+                const uint32_t hi = (pass == 0) ? 0u : (k >> (shift + 8));
+                const uint32_t d = (k >> shift) & 0xffu;
+                if (hi == pre0) {
+                    if (d == run_d0) {
+                        ++run_c0;
+                    } else {
+                        if (run_c0) atomicAdd(&hist[run_d0 * 32 + lane], run_c0);
+                        run_d0 = d;
+                        run_c0 = 1u;
+                    }
+                }
+                if (!same && hi == pre1) {
+                    if (d == run_d1) {
+                        ++run_c1;
+                    } else {
+                        if (run_c1) atomicAdd(&hist[(256 + run_d1) * 32 + lane], run_c1);
+                        run_d1 = d;
+                        run_c1 = 1u;
+                    }
                 }
             }
         }
+        if (run_c0) atomicAdd(&hist[run_d0 * 32 + lane], run_c0);
+        if (run_c1) atomicAdd(&hist[(256 + run_d1) * 32 + lane], run_c1);
         __syncthreads();
         // per gene and tracked order statistic: the bin that holds the wanted rank
         if (warp < 2) {

@@ -483,12 +483,28 @@ class AsyncUpload:
     """A dense host matrix on its way to the device: row chunks copied LAST ROWS FIRST on a side stream,
     one event per chunk.  ``chunks`` = [(row_lo, row_hi, event)] in upload order."""
 
-    def __init__(self, Xd, chunks, keep):
-        self.Xd, self.chunks, self._keep = Xd, chunks, keep
+    def __init__(self, Xd, host, side, pending):
+        self.Xd, self._host, self._side, self._pending = Xd, host, side, list(pending)
+        self.chunks = []
         self.shape = tuple(Xd.shape)
+
+    def enqueue(self, n_chunks=None):
+        """Queue the next ``n_chunks`` row chunks (all that are left if None) on the side stream.
+        The copy engine serves transfers in issue order, whatever their stream: everything queued
+        here delays the small label arrays the first kernels wait for, so start_upload() queues only
+        the part that the host's label encoding hides and the pipeline queues the rest afterwards."""
+        n = len(self._pending) if n_chunks is None else min(int(n_chunks), len(self._pending))
+        with torch.cuda.stream(self._side):
+            for _ in range(n):
+                lo, hi = self._pending.pop(0)
+                self.Xd[lo:hi].copy_(self._host[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+                self.chunks.append((lo, hi, ev))
 
     def event_for_rows_from(self, row_lo: int):
         """Event after which every input row >= row_lo is on the device."""
+        self.enqueue()
         ev = self.chunks[-1][2]
         for lo, _hi, e in self.chunks:
             if lo <= row_lo:
@@ -497,15 +513,20 @@ class AsyncUpload:
         return ev
 
     def wait_all(self):
+        self.enqueue()
         torch.cuda.current_stream().wait_event(self.chunks[-1][2])
         return self.Xd
 
 
-# Measured at config 2 (1.6 GB matrix, B200, PCIe Gen5): the plain upload already hides behind the host's
-# label encoding and the first kernels, and eight smaller launches per pass cost as much as the overlap
-# wins (e2e 123.6 ms plain vs 127.9 ms streamed), so the streamed path is opt-in (MN_STREAM_CHUNKS > 1).
+# Measured at config 2 (1.6 GB pinned matrix, B200, ~55 GB/s H2D), median of 8 calls of the public API:
+# upload-then-compute 123.5 ms; 16 upload chunks x 4 row chunks of the passes 109.8 ms (x 8: 112.1, x 16: 114.7).
+# The first streamed version gained nothing: all chunk copies were queued up front and the copy engine, which
+# serves transfers in issue order across streams, made the small label arrays -- which the first kernel
+# needs -- wait for the whole matrix.  MN_STREAM_CHUNKS=1 turns streaming off.
 STREAM_MIN_BYTES = 64 << 20
-STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "1"))
+STREAM_EARLY_BYTES = 400 << 20          # queued before the host encodes labels (~8 ms of PCIe Gen5)
+STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "16"))
+STREAM_DEV_CHUNKS = int(_os.environ.get("MN_STREAM_DEV_CHUNKS", "4"))     # row chunks of the passes; 0 = as many as uploads
 
 
 def start_upload(X):
@@ -523,17 +544,11 @@ def start_upload(X):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             bounds = [int(round(k * N / STREAM_CHUNKS)) for k in range(STREAM_CHUNKS + 1)]
-            chunks = []
-            with torch.cuda.stream(side):
-                for k in reversed(range(STREAM_CHUNKS)):
-                    lo, hi = bounds[k], bounds[k + 1]
-                    if hi > lo:
-                        Xd[lo:hi].copy_(t[lo:hi], non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(side)
-                        chunks.append((lo, hi, ev))
+            pending = [(bounds[k], bounds[k + 1]) for k in reversed(range(STREAM_CHUNKS)) if bounds[k + 1] > bounds[k]]
             Xd.record_stream(side)
-            return AsyncUpload(Xd, chunks, t)
+            up = AsyncUpload(Xd, t, side, pending)
+            up.enqueue(max(1, int(round(STREAM_EARLY_BYTES / max(1, X.nbytes // STREAM_CHUNKS)))))
+            return up
     return to_device_matrix(X)
 
 
@@ -550,7 +565,8 @@ def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins
     cur = torch.cuda.current_stream()
     perm_np = np.asarray(lay.perm)
     perm, cell_label, seg_off = _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off)
-    nd = max(1, min(STREAM_CHUNKS, N // 4096))
+    up.enqueue()                                 # the rest of the matrix follows the small arrays through the copy engine
+    nd = max(1, min(STREAM_DEV_CHUNKS if STREAM_DEV_CHUNKS > 0 else STREAM_CHUNKS, N // 4096))
     bounds = sorted(set([0, N] + [min(N, int(round(k * N / nd / 256.0)) * 256) for k in range(1, nd)]))
     nd = len(bounds) - 1
     # lowest input row that device rows >= b need
