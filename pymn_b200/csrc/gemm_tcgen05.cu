@@ -948,16 +948,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 // Data path: each warp owns a 4 KB shared-memory slot; one lane fetches the warp's next chunk with a
 // bulk async copy (cp.async.bulk, mbarrier completion) as soon as the current one has been moved to
 // registers, so the HBM latency hides behind the ~600 instructions a chunk costs and no registers are
-// spent on prefetching: 24 warps per SM fit.  The kernel is bound by shared-memory lookups (one
+// spent on prefetching: 20 warps per SM at 96 registers (the column sums live in shared memory too).  The kernel is bound by shared-memory lookups (one
 // random-bank LDS per pair, ~3.5-way conflicts) and latency, not by HBM.
-constexpr int SPILL_WARPS = 24;
+constexpr int SPILL_WARPS = 24;          // most the slots allow; the launcher's default is 20 (96 registers, measured best)
 __device__ __forceinline__ void bulk_load_4k(void* smem_dst, const void* gsrc, uint64_t* bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 4096;" ::"r"(smem_u32(bar)) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 4096, [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(smem_u32(bar)) : "memory");
 }
-template <int BN>
-__global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const GemmParams p, int tb) {
+template <int BN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) vote_spill_kernel(const GemmParams p, int tb) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     constexpr int HALF_COLS = BN / 2;
     constexpr int NCH = HALF_COLS / 32;         // chunks per column half
@@ -966,7 +966,12 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint4* s_slot = reinterpret_cast<uint4*>(s_raw) + (size_t)warp * 256;                    // this warp's 4 KB slot
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_raw + (size_t)n_warps * 4096) + warp;
-    uint32_t* s_table = reinterpret_cast<uint32_t*>(s_raw + (size_t)n_warps * 4096 + (size_t)n_warps * 8);   // [nbins + 2]
+    // column sums carried across a run of tiles: [chunk][lane] per warp, in shared memory -- registers are
+    // what limits the overlap of the table lookups (at 80 registers the compiler funnelled all 32 lookups of a
+    // chunk through one temporary, exposing the full LDS latency 32 times)
+    unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_raw + (size_t)n_warps * (4096 + 8)) +
+                                (size_t)warp * (NCK * 32) + lane;
+    uint32_t* s_table = reinterpret_cast<uint32_t*>(s_raw + (size_t)n_warps * (4096 + 8 + NCK * 32 * 8));   // [nbins + 2]
     for (int i = threadIdx.x; i < p.nbins + 2; i += blockDim.x) s_table[i] = lut_pack(p.lut, i, p.nbins);
     const bool wide = p.lut[p.nbins + 1] != 0u;
     if (lane == 0) {
@@ -995,22 +1000,18 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
     int blk = gw >> 2;
     if (blk < n_blocks && lane == 0) bulk_load_4k(s_slot, chunk_src(blk * tb, 0), s_bar);
     // column side carried across tiles
-    unsigned long long colacc[NCK];
 #pragma unroll
-    for (int k = 0; k < NCK; ++k) colacc[k] = 0ull;
+    for (int k = 0; k < NCK; ++k) s_col[k * 32] = 0ull;
     int64_t col_n0 = -1;
     int col_lab = 0;
-    int lab_c[NCK];                  // label of column n0 + 32 k + lane
-#pragma unroll
-    for (int k = 0; k < NCK; ++k) lab_c[k] = 0;
-    int64_t lab_n0 = -1;
 
     auto flush_cols = [&]() {
         if (col_n0 >= 0) {
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < NCK; ++k) {
-                if (colacc[k]) red_add_u64_hint(p.votes + (col_n0 + 32 * k + lane) * (int64_t)p.L + col_lab, colacc[k], pol_ef);
-                colacc[k] = 0ull;
+                const unsigned long long v = s_col[k * 32];
+                if (v) red_add_u64_hint(p.votes + (col_n0 + 32 * k + lane) * (int64_t)p.L + col_lab, v, pol_ef);
+                s_col[k * 32] = 0ull;
             }
         }
         col_n0 = -1;
@@ -1026,14 +1027,6 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
             const int64_t m0 = (int64_t)it.mt * (BM * p.ctas) + (int64_t)gr * BM, n0 = (int64_t)it.nt() * BN;
             const int64_t m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
-            if (n0 != lab_n0) {
-#pragma unroll
-                for (int k = 0; k < NCK; ++k) {
-                    const int64_t n = n0 + 32 * k + lane;
-                    lab_c[k] = n < p.N ? p.label[n] : -1 - k;       // columns past the end: a run of their own (zero weights)
-                }
-                lab_n0 = n0;
-            }
             VoteRows vr;
             vr.begin(p.label[row_ok ? m : p.M - 1], p.votes + (row_ok ? m : 0) * (int64_t)p.L, lane);
             if (col_n0 >= 0 && (col_n0 != n0 || col_lab != vr.lab_i || !vr.warp_uniform)) flush_cols();
@@ -1042,11 +1035,14 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
                 col_lab = vr.lab_i;
             }
             // NOT unrolled: eight copies of the chunk body (~6,000 instructions each) overflow the instruction
-            // cache -- ncu showed "no instruction" as the top stall of the unrolled version.  lab_c / colacc
-            // stay in registers through compile-time indexed select / predicated-add chains.
+            // cache -- ncu showed "no instruction" as the top stall of the unrolled version.
 #pragma unroll 1
             for (int k = 0; k < NCK; ++k) {
                 uint32_t r[32];
+                // labels of this chunk's columns and of the column before each (L1-resident; issued before the wait)
+                const int64_t n = n0 + 32 * k + lane;
+                const int lab_k = n < p.N ? __ldg(p.label + n) : -1 - k;      // past the end: a run of its own (zero weights)
+                const int lab_prev = (n >= 1 && n - 1 < p.N) ? __ldg(p.label + n - 1) : -1 - k;
                 mbar_wait(s_bar, phase);
                 phase ^= 1u;
 #pragma unroll
@@ -1071,22 +1067,11 @@ __global__ void __launch_bounds__(SPILL_WARPS * 32, 1) vote_spill_kernel(const G
                     bulk_load_4k(s_slot, chunk_src(nt_tile, nk), s_bar);
                 }
                 // label runs of this chunk's columns: a run starts where the label differs from the previous column's
-                int lab_k = lab_c[0], lab_km1 = lab_c[0];
-#pragma unroll
-                for (int kk = 1; kk < NCK; ++kk) {
-                    lab_k = (kk == k) ? lab_c[kk] : lab_k;
-                    lab_km1 = (kk == k - 1) ? lab_c[kk] : lab_km1;
-                }
-                int prev = __shfl_up_sync(0xffffffffu, lab_k, 1);
-                const int prev_chunk_last = __shfl_sync(0xffffffffu, lab_km1, 31);
-                if (lane == 0) prev = prev_chunk_last;
-                const unsigned brk = __ballot_sync(0xffffffffu, (k == 0 && lane == 0) || prev != lab_k);
+                const unsigned brk = __ballot_sync(0xffffffffu, (k == 0 && lane == 0) || lab_prev != lab_k);
                 const int lab_use = lab_k < 0 ? 0 : lab_k;
                 const uint32_t mycol = vr.chunk(r, brk, LaneLabels{lab_use}, s_table, wide, true,
                                                 p.votes + (n0 + 32 * k) * (int64_t)p.L, p.L, pol_ef, lane);
-#pragma unroll
-                for (int kk = 0; kk < NCK; ++kk)
-                    if (kk == k) colacc[kk] += mycol;
+                if (mycol) s_col[k * 32] += mycol;
             }
             vr.finish();
         }
@@ -1249,14 +1234,15 @@ static int corr_ctas(bool wide) { return (wide && !getenv("MN_GEMM_1CTA")) ? 2 :
 
 template <int BN>
 static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
-    int warps = SPILL_WARPS;
-    if (const char* e = getenv("MN_SPILL_WARPS")) {    // experiment knob (multiple of 4)
+    int warps = 20;
+    if (const char* e = getenv("MN_SPILL_WARPS")) {    // tuning knob (multiple of 4): 16 / 20 / 24 measured 22.4 / 21.4 / 22.6 ms at config 2
         const int v = atoi(e);
         if (v >= 4 && v <= SPILL_WARPS && (v & 3) == 0) warps = v;
     }
-    // per warp a 4 KB slot + its mbarrier, then the packed LUT
-    const size_t smem = (size_t)warps * (4096 + 8) + (size_t)((p.nbins + 2 + 3) & ~3) * 4;
-    auto kern = vote_spill_kernel<BN>;
+    // per warp a 4 KB slot, its mbarrier and its column sums (8 chunks x 32 lanes x 8 B), then the packed LUT
+    const size_t smem = (size_t)warps * (4096 + 8 + (BN / 32) * 32 * 8) + (size_t)((p.nbins + 2 + 3) & ~3) * 4;
+    // (the register budget per thread follows the warp count: 24 warps -> 80, 20 -> 96, 16 -> 128)
+    auto kern = warps > 20 ? vote_spill_kernel<BN, 24> : (warps > 16 ? vote_spill_kernel<BN, 20> : vote_spill_kernel<BN, 16>);
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // tiles per run: the column sums are flushed about once per run, so long runs are cheaper (64 = one
     // column segment of a band), but every warp should still get >= 8 runs to balance the grid
