@@ -266,7 +266,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    h2d = int(N) * int(G) * 4 + int(N) * 4 * 3 + (S + 1) * 4
+    # (N > 1: every rank uploads its own 1/N slice of the matrix -- the total over ranks is the matrix once --
+    #  plus the small label arrays on every rank)
+    h2d = int(N) * int(G) * 4 + world * (int(N) * 4 * 3 + (S + 1) * 4)
     d2h = L * L * 8 + L * 4 + int(N)
     # the API result must equal the device-resident result (same kernels, same inputs)
     order = np.argsort(lay.sorted_pos)

@@ -444,11 +444,18 @@ def us_default_device(Xd, perm, cell_label, seg_off, L, S, ndn=True, nbins=DEFAU
                       spill_tiles=None):
     """Device-resident full-network pipeline: every argument already lives in HBM.
     Returns (auroc float64 [L, L] rows = test labels, n_pos, flags, hist)."""
-    rank, world, reduce_fn = shard if shard is not None else dist_shard()
     t = timer
     if t: t.start("rank_normalize")
     rc = rank_normalize(Xd, row_index=perm, drop_mode=0)
     if t: t.stop("rank_normalize")
+    return network_from_ranked(rc, cell_label, seg_off, L, S, ndn, nbins, shard, timer, spill_tiles)
+
+
+def network_from_ranked(rc: RankedCells, cell_label, seg_off, L, S, ndn=True, nbins=DEFAULT_NBINS, shard=None,
+                        timer=None, spill_tiles=None):
+    """Pass 1 -> LUT -> pass 2 -> votes -> AUROC on ranked cells that are already in label-sorted order."""
+    rank, world, reduce_fn = shard if shard is not None else dist_shard()
+    t = timer
     dev = rc.d_hi.device
     N = rc.M
     hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
@@ -523,6 +530,7 @@ class AsyncUpload:
 # The first streamed version gained nothing: all chunk copies were queued up front and the copy engine, which
 # serves transfers in issue order across streams, made the small label arrays -- which the first kernel
 # needs -- wait for the whole matrix.  MN_STREAM_CHUNKS=1 turns streaming off.
+SHARD_UPLOAD = _os.environ.get("MN_SHARD_UPLOAD", "1") != "0"     # multi-GPU: each rank uploads only its slice of the cells
 STREAM_MIN_BYTES = 64 << 20
 STREAM_EARLY_BYTES = 400 << 20          # queued before the host encodes labels (~8 ms of PCIe Gen5)
 STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "16"))
@@ -534,6 +542,13 @@ def start_upload(X):
     is sent in row chunks, last rows first, on a side stream (AsyncUpload): the full-network pipeline
     starts ranking and correlating the last cells while the first ones are still crossing PCIe
     (us_default_streamed).  Anything else goes through to_device_matrix."""
+    rank, world, _ = dist_shard()
+    if (world > 1 and SHARD_UPLOAD and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
+            and X.flags.c_contiguous and X.shape[0] >= 4 * world):
+        N = int(X.shape[0])
+        per = (N + world - 1) // world
+        lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+        return ShardedUpload(to_device(X[lo:hi], torch.float32), lo, hi, tuple(X.shape), rank, world, per)
     if (STREAM_CHUNKS > 1 and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
             and X.flags.c_contiguous and X.nbytes >= STREAM_MIN_BYTES):
         t = torch.from_numpy(X)
@@ -607,12 +622,54 @@ def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins
     return auc, n_pos, rc.flags, hist
 
 
+class ShardedUpload:
+    """Multi-GPU ingestion: this rank uploads only ITS slice of the cells (rows [lo, hi) of the host matrix,
+    input order); the ranked fp16 planes are exchanged over NVLink afterwards (us_default_sharded)."""
+
+    def __init__(self, X_local, lo, hi, shape, rank, world, per):
+        self.X_local, self.lo, self.hi, self.shape = X_local, lo, hi, shape
+        self.rank, self.world, self.per = rank, world, per
+
+
+def us_default_sharded(sh: ShardedUpload, lay: LabelLayout, L, S, ndn=True, nbins=DEFAULT_NBINS):
+    """Full-network pipeline with data-parallel ingestion: every rank ranks the cells of its own
+    input slice (K1, input order), one NCCL all-gather makes the fp16 planes (0.8 GB at config 2, ~ms over
+    NVLink instead of N x the matrix over PCIe) and scales available everywhere, a row gather puts them
+    into label-sorted order, and the passes run sharded by row tile as before.  K1 is row-wise, so the
+    planes -- and therefore the tables -- are identical to the single-GPU ones."""
+    import torch.distributed as dist
+    rank, world, reduce_fn = dist_shard()
+    N, G = sh.shape
+    per = sh.per
+    rc_loc = rank_normalize(sh.X_local, drop_mode=0)
+    dev = rc_loc.d_hi.device
+    n_loc = sh.hi - sh.lo
+
+    def gather(t_loc, width, dtype):
+        buf = torch.zeros((per,) + ((width,) if width else ()), dtype=dtype, device=dev)
+        buf[:n_loc] = t_loc
+        out = torch.empty((world * per,) + ((width,) if width else ()), dtype=dtype, device=dev)
+        dist.all_gather_into_tensor(out, buf)
+        return out
+
+    perm = to_device(np.asarray(lay.perm, dtype=np.int64))
+    d_hi = gather(rc_loc.d_hi, rc_loc.ldd, torch.float16).index_select(0, perm)
+    d_lo = gather(rc_loc.d_lo, rc_loc.ldd, torch.float16).index_select(0, perm) if rc_loc.d_lo is not None else None
+    inv_norm = gather(rc_loc.inv_norm, 0, torch.float32).index_select(0, perm)
+    flags = gather(rc_loc.flags, 0, torch.uint8).index_select(0, perm)
+    rc = RankedCells(d_hi, d_lo, rc_loc.ldd, inv_norm, flags, N, G)
+    return network_from_ranked(rc, _i32(lay.cell_label), _i32(lay.seg_off), L, S, ndn, nbins,
+                               (rank, world, reduce_fn))
+
+
 def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):
     """metaNeighborUS_default.  Returns dict(auroc [L, L] rows = TEST labels, cols = TRAIN
     labels, both in row order -- the caller transposes / reorders, MetaNeighborUS.py:213).
     X: host / device matrix, CsrMatrix, or an AsyncUpload from start_upload()."""
     L, S = len(lay.row_labels), len(lay.studies)
-    if isinstance(X, AsyncUpload):
+    if isinstance(X, ShardedUpload):
+        auc, n_pos, flags, hist = us_default_sharded(X, lay, L, S, ndn, nbins)
+    elif isinstance(X, AsyncUpload):
         auc, n_pos, flags, hist = us_default_streamed(X, lay, L, S, ndn, nbins)
     else:
         Xd = to_device_matrix(X)

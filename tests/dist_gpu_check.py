@@ -31,6 +31,19 @@ def main():
     single = engine.us_default_device(*args, shard=(0, 1, None))[0].cpu().numpy()
     assert np.array_equal(multi, single, equal_nan=True), "sharded full-network table differs from the single-GPU one"
 
+    # public API, full network: every rank uploads only its slice of the cells, planes are all-gathered
+    genes0 = np.array([f"g{i}" for i in range(300)], dtype=object)
+    inp0 = dict(X=x, study=s, ctype=c, genes=genes0, hvg=np.ones(300, bool))
+    kw = dict(fast_version=False, symmetric_output=False, save_uns=False)
+    api_multi = pymn_b200.MetaNeighborUS(make_adata(inp0), "study_id", "cell_type", **kw)
+    saved_shard = engine.dist_shard
+    engine.dist_shard = lambda: (0, 1, None)
+    try:
+        api_single = pymn_b200.MetaNeighborUS(make_adata(inp0), "study_id", "cell_type", **kw)
+    finally:
+        engine.dist_shard = saved_shard
+    assert np.array_equal(api_multi.values, api_single.values, equal_nan=True), "sharded-ingestion table differs"
+
     # centroid (fast) path: train columns are dealt to the ranks, tables all-gathered
     for ovb in (False, True):
         sharded = engine.us_fast(x, lay, True, ovb)
