@@ -545,9 +545,7 @@ def start_upload(X):
     rank, world, _ = dist_shard()
     if (world > 1 and SHARD_UPLOAD and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
             and X.flags.c_contiguous and X.shape[0] >= 4 * world):
-        N = int(X.shape[0])
-        per = (N + world - 1) // world
-        lo, hi = min(N, rank * per), min(N, (rank + 1) * per)
+        lo, hi, per = shard_rows(X.shape[0], rank, world)
         return ShardedUpload(to_device(X[lo:hi], torch.float32), lo, hi, tuple(X.shape), rank, world, per)
     if (STREAM_CHUNKS > 1 and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
             and X.flags.c_contiguous and X.nbytes >= STREAM_MIN_BYTES):
@@ -622,6 +620,23 @@ def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins
     return auc, n_pos, rc.flags, hist
 
 
+def shard_rows(N: int, rank: int, world: int):
+    """Rows [lo, hi) of the input a rank ingests, and the common block size `per` (the all-gather needs equal
+    blocks: rank r's block starts at r * per, so gathered row j is input row j; the tail is padding)."""
+    per = (int(N) + world - 1) // world
+    return min(int(N), rank * per), min(int(N), (rank + 1) * per), per
+
+
+def gather_rows(local: torch.Tensor, per: int, world: int) -> torch.Tensor:
+    """All-gather per-rank row blocks (zero-padded to `per` rows) into [world * per, ...]."""
+    import torch.distributed as dist
+    buf = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf)
+    return out
+
+
 class ShardedUpload:
     """Multi-GPU ingestion: this rank uploads only ITS slice of the cells (rows [lo, hi) of the host matrix,
     input order); the ranked fp16 planes are exchanged over NVLink afterwards (us_default_sharded)."""
@@ -637,26 +652,15 @@ def us_default_sharded(sh: ShardedUpload, lay: LabelLayout, L, S, ndn=True, nbin
     NVLink instead of N x the matrix over PCIe) and scales available everywhere, a row gather puts them
     into label-sorted order, and the passes run sharded by row tile as before.  K1 is row-wise, so the
     planes -- and therefore the tables -- are identical to the single-GPU ones."""
-    import torch.distributed as dist
     rank, world, reduce_fn = dist_shard()
     N, G = sh.shape
     per = sh.per
     rc_loc = rank_normalize(sh.X_local, drop_mode=0)
-    dev = rc_loc.d_hi.device
-    n_loc = sh.hi - sh.lo
-
-    def gather(t_loc, width, dtype):
-        buf = torch.zeros((per,) + ((width,) if width else ()), dtype=dtype, device=dev)
-        buf[:n_loc] = t_loc
-        out = torch.empty((world * per,) + ((width,) if width else ()), dtype=dtype, device=dev)
-        dist.all_gather_into_tensor(out, buf)
-        return out
-
     perm = to_device(np.asarray(lay.perm, dtype=np.int64))
-    d_hi = gather(rc_loc.d_hi, rc_loc.ldd, torch.float16).index_select(0, perm)
-    d_lo = gather(rc_loc.d_lo, rc_loc.ldd, torch.float16).index_select(0, perm) if rc_loc.d_lo is not None else None
-    inv_norm = gather(rc_loc.inv_norm, 0, torch.float32).index_select(0, perm)
-    flags = gather(rc_loc.flags, 0, torch.uint8).index_select(0, perm)
+    d_hi = gather_rows(rc_loc.d_hi, per, world).index_select(0, perm)
+    d_lo = gather_rows(rc_loc.d_lo, per, world).index_select(0, perm) if rc_loc.d_lo is not None else None
+    inv_norm = gather_rows(rc_loc.inv_norm, per, world).index_select(0, perm)
+    flags = gather_rows(rc_loc.flags, per, world).index_select(0, perm)
     rc = RankedCells(d_hi, d_lo, rc_loc.ldd, inv_norm, flags, N, G)
     return network_from_ranked(rc, _i32(lay.cell_label), _i32(lay.seg_off), L, S, ndn, nbins,
                                (rank, world, reduce_fn))

@@ -51,3 +51,32 @@ def test_geneset_sharding_gloo(tmp_path, n_sets):
         got = np.load(tmp_path / f"full_{rank}.npy")
         assert np.array_equal(got, want, equal_nan=True)
         assert np.array_equal(np.load(tmp_path / f"sum_{rank}.npy"), np.full(5, 3))
+
+
+def _worker_rows(rank, world, port, n, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pymn_b200 import engine
+        full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)       # every rank holds the same host matrix
+        lo, hi, per = engine.shard_rows(n, rank, world)
+        got = engine.gather_rows(full[lo:hi].clone(), per, world)           # what us_default_sharded does with the planes
+        vec = engine.gather_rows(full[lo:hi, 0].clone(), per, world)
+        np.save(os.path.join(out_dir, f"rows_{rank}.npy"), got.numpy())
+        np.save(os.path.join(out_dir, f"vec_{rank}.npy"), vec.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 7, 2])
+def test_sharded_ingestion_row_gather_gloo(tmp_path, n):
+    """Data-parallel ingestion: each rank contributes its row slice; after the all-gather row j of the buffer is
+    input row j on every rank (ragged last block padded), so `index_select(perm)` yields the label-sorted order."""
+    world = 2
+    mp.spawn(_worker_rows, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    want = np.arange(n * 3, dtype=np.float32).reshape(n, 3)
+    for rank in range(world):
+        got = np.load(tmp_path / f"rows_{rank}.npy")
+        assert got.shape[0] >= n and np.array_equal(got[:n], want) and not got[n:].any()
+        assert np.array_equal(np.load(tmp_path / f"vec_{rank}.npy")[:n], want[:, 0])
