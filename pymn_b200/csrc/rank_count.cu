@@ -28,13 +28,16 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                   float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode, CsrIn csr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)RC_HB * 4 + (size_t)g_pad * 2;
-    uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw + wib * per_warp);     // histogram, then 2*rank table
-    uint16_t* vals = reinterpret_cast<uint16_t*>(tab + RC_HB);                   // the row as uint16
+    // 16-bit bins (counts <= G and 2*rank <= 2G + 1 fit for G < 32,768; the launcher checks): two per word,
+    // incremented with a 32-bit shared atomic on the right half.  8 KB per warp instead of 12 -> 28 warps/SM.
+    const size_t per_warp = (size_t)RC_HB * 2 + (size_t)g_pad * 2;
+    uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem_raw + wib * per_warp);   // histogram, then 2*rank table
+    uint16_t* tab = reinterpret_cast<uint16_t*>(tab32);
+    uint16_t* vals = tab + RC_HB;                                                // the row as uint16
     const int64_t warps_total = (int64_t)gridDim.x * RC_WARPS;
     const bool vec4 = (col_index == nullptr) && ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
 
-    for (int b = lane; b < RC_HB; b += 32) tab[b] = 0u;
+    for (int b = lane; b < RC_HB / 2; b += 32) tab32[b] = 0u;
     __syncwarp();
 
     for (int64_t row = (int64_t)blockIdx.x * RC_WARPS + wib; row < M; row += warps_total) {
@@ -65,7 +68,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                     ok = ok && ((unsigned)iv < (unsigned)RC_HB) && ((float)iv == f[u]) && ((unsigned)jj[u] < (unsigned)G);
                     iv = min(max(iv, 0), RC_HB - 1);
                     if (iv > 0) {
-                        atomicAdd(&tab[iv], 1u);
+                        atomicAdd(&tab32[iv >> 1], 1u << ((iv & 1) << 4));
                         ++nnz;
                         maxv = max(maxv, iv);
                         vals[min(max(jj[u], 0), G - 1)] = (uint16_t)iv;
@@ -96,7 +99,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                             ok = ok && ((unsigned)iv[t] < (unsigned)RC_HB) && ((float)iv[t] == f[t]);
                             iv[t] = min(max(iv[t], 0), RC_HB - 1);
                             if (iv[t] > 0) {
-                                atomicAdd(&tab[iv[t]], 1u);
+                                atomicAdd(&tab32[iv[t] >> 1], 1u << ((iv[t] & 1) << 4));
                                 ++nnz;
                                 maxv = max(maxv, iv[t]);
                             }
@@ -113,7 +116,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                 ok = ok && ((unsigned)iv < (unsigned)RC_HB) && ((float)iv == f);
                 iv = min(max(iv, 0), RC_HB - 1);
                 if (iv > 0) {
-                    atomicAdd(&tab[iv], 1u);
+                    atomicAdd(&tab32[iv >> 1], 1u << ((iv & 1) << 4));
                     ++nnz;
                     maxv = max(maxv, iv);
                 }
@@ -127,7 +130,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
                 ok = ok && ((unsigned)iv < (unsigned)RC_HB) && ((float)iv == f);
                 iv = min(max(iv, 0), RC_HB - 1);
                 if (iv > 0) {
-                    atomicAdd(&tab[iv], 1u);
+                    atomicAdd(&tab32[iv >> 1], 1u << ((iv & 1) << 4));
                     ++nnz;
                     maxv = max(maxv, iv);
                 }
@@ -143,7 +146,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
         __syncwarp();
         if (!ok) {
             // not a row of small non-negative integers: hand it to the sorting kernel
-            for (int b = 1 + lane; b <= maxv; b += 32) tab[b] = 0u;
+            for (int b = lane; b <= (maxv >> 1); b += 32) tab32[b] = 0u;
             if (lane == 0) flags[row] = 16;
             __syncwarp();
             continue;
@@ -165,7 +168,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
             }
             if (b <= maxv) {
                 const int r2 = 2 * (nzero + below + inc - cnt) + cnt + 1;
-                tab[b] = (uint32_t)r2;
+                tab[b] = (uint16_t)r2;
                 const long long d = (long long)r2 - c;             // all cnt entries of this value share d
                 ss += (unsigned long long)(d * d) * (unsigned long long)cnt;
             }
@@ -219,7 +222,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
             }
         }
         __syncwarp();
-        for (int b = 1 + lane; b <= maxv; b += 32) tab[b] = 0u;        // leave the histogram clean for the next row
+        for (int b = lane; b <= (maxv >> 1); b += 32) tab32[b] = 0u;   // leave the histogram clean for the next row
         __syncwarp();
     }
 }
@@ -228,7 +231,11 @@ int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, con
                       __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
                       int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr) {
     const int g_pad = (G + 7) & ~7;
-    const size_t per_warp = (size_t)RC_HB * 4 + (size_t)g_pad * 2;
+    if (G >= 32768) {
+        set_error("rank_count: G=%d exceeds the 16-bit rank table (max 32767)", G);
+        return 1;
+    }
+    const size_t per_warp = (size_t)RC_HB * 2 + (size_t)g_pad * 2;
     const size_t smem = per_warp * RC_WARPS;
     static size_t configured = 0;
     if (smem > 40 * 1024 && smem > configured) {
@@ -239,7 +246,7 @@ int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t blocks = (M + RC_WARPS - 1) / RC_WARPS;
-    const int64_t max_blocks = (int64_t)sms * 8;
+    const int64_t max_blocks = (int64_t)sms * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     rank_count_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(X, ldx, row_index, col_index, M, G, g_pad, d_hi, d_lo,
                                                                    ldd, inv_norm, flags, xnorm, rank2, drop_mode, csr);
