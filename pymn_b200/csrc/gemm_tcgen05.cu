@@ -174,10 +174,21 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
 }
-// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+// ... and the same tile delivered to several CTAs of the cluster (bit r of cta_mask = CTA rank r): one L2 read,
+// the bytes are counted on the barrier at this offset in the pair leader of every destination
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                    uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(cta_mask),
+          "r"(c0), "r"(c1)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in the CTAs of cta_mask
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -241,7 +252,8 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
 __device__ __forceinline__ void red_add_u64_hint(unsigned long long* addr, unsigned long long val, uint64_t pol) {
     asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(addr), "l"(val), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+template <int THREADS = EPI_THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 // K-major, 128B-swizzled operand tile: 8-row groups of 1024 bytes (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -505,19 +517,32 @@ struct TileIter {
 // the 128 B/clk shared-memory bandwidth for the MMA reads alone and tops out near 2/3 of the tensor
 // peak once TMA writes and the epilogue's lookups share the same pipe.  Only the leader (rank 0)
 // claims tiles and issues MMAs; completion is multicast to the barriers of both CTAs.
-template <int BN, int EPI, int NCHAIN, int CTAS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW = epilogue warps: 8 (two per TMEM lane quarter, each half of the tile's columns), or 16 for the pass-1
+// epilogue (four per quarter, a quarter of the columns each; opt-in MN_HIST_EW16).  Measured at config 2:
+// 16 warps are no faster (73.0 vs 70.8 ms), and dropping the histogram atomics altogether changes nothing
+// (72.8 vs 72.9 ms): the epilogue is not what paces pass 1 -- the power cap is.
+template <int BN, int EPI, int NCHAIN, int CTAS, int EW = EPI_WARPS>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
             const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr bool PAIR = (CTAS == 2);
-    constexpr int B_ROWS = BN / CTAS;              // rows of the B tile this CTA stages
+    // CTAS = 4 (opt-in, MN_GEMM_CTAS=4): two such pairs stacked in M form one cluster and work on a 512 x BN
+    // tile.  Both pairs need the same B tile: pair 0 loads it ONCE with TMA multicast into the shared memory of
+    // both pairs (CTA r of pair 0 -> CTAs r and r + 2), 768 instead of 1,024 operand rows per 512 x 256 outputs.
+    // Correct (same tests) but measured slower than pairs: see corr_ctas().
+    constexpr bool PAIR = (CTAS >= 2);
+    constexpr bool QUAD = (CTAS == 4);
+    static_assert(CTAS == 1 || CTAS == 2 || CTAS == 4, "1 CTA, a pair, or two pairs");
+    constexpr int B_ROWS = BN / (PAIR ? 2 : 1);    // rows of the B tile this CTA stages
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
-    const bool leader = cta_rank == 0u;
+    const bool leader = cta_rank == 0u;                     // cluster leader: claims tiles
+    const uint32_t pair_rank = cta_rank & 1u;               // rank inside the CTA pair
+    const uint32_t pair_lead = cta_rank & ~1u;              // cluster rank of this pair's leader (issues the MMAs)
+    const bool pair_leader = pair_rank == 0u;
     // NCHAIN independent accumulators per tile (k-blocks dealt round-robin, summed in FP32 by the
     // epilogue): the tensor core truncates when it adds into a long FP32 chain, so shorter chains
     // cut the accumulation bias NCHAIN-fold.  Two tiles in flight when TMEM (512 columns) allows.
@@ -538,9 +563,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     int32_t* s_lab = reinterpret_cast<int32_t*>(s_invb + BN);              // [BN]
     float* s_add = reinterpret_cast<float*>(s_lab + BN);                   // [BN] (EPI_STORE) / flush masks (EPI_VOTE)
     uint32_t* s_flush = reinterpret_cast<uint32_t*>(s_add);
-    uint32_t* s_colw = reinterpret_cast<uint32_t*>(s_add + BN);            // [EPI_WARPS][BN/2] column sums (EPI_VOTE)
-    int32_t* s_wlab = reinterpret_cast<int32_t*>(s_colw + EPI_WARPS * (BN / 2));   // [EPI_WARPS] row label of a uniform warp
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_wlab + EPI_WARPS);
+    static_assert(EW == 8 || (EW == 16 && EPI == EPI_HIST), "16 epilogue warps are wired for the pass-1 epilogue only");
+    constexpr int EPI_T = EW * 32;                                         // epilogue threads of this instantiation
+    constexpr int ALL_T = 64 + EPI_T;
+    uint32_t* s_colw = reinterpret_cast<uint32_t*>(s_add + BN);            // [EW][BN/2] column sums (EPI_VOTE)
+    int32_t* s_wlab = reinterpret_cast<int32_t*>(s_colw + EW * (BN / 2));  // [EW] row label of a uniform warp
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_wlab + EW);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + MAX_STAGES;
     uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
@@ -562,16 +590,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], QUAD ? 2 : 1);        // quad: both pairs must have consumed the shared B slot
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], EPI_WARPS * CTAS);   // the leader's MMA thread waits for the epilogues of both CTAs
+            mbar_init(&tempty_bar[a], EW * (PAIR ? 2 : 1));    // a pair leader's MMA thread waits for the epilogues of both its CTAs
         }
         for (int qi = 0; qi < TQ; ++qi) {
             mbar_init(&qfull_bar[qi], 1);
-            // leader: MMA thread + one lane of every epilogue warp (+ the peer's producer and epilogue warps)
-            mbar_init(&qempty_bar[qi], 1 + EPI_WARPS + (PAIR ? 1 + EPI_WARPS : 0));
+            // cluster leader: every consumer of a queue slot in the cluster -- per CTA one lane of every epilogue
+            // warp, the producers of the non-leader CTAs, the MMA thread of every pair leader
+            mbar_init(&qempty_bar[qi], CTAS * EW + (CTAS - 1) + (QUAD ? 2 : 1));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -586,7 +615,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     }
     if (EPI != EPI_STORE) {
         // hist starts at zero; lut is copied in
-        for (int i = threadIdx.x; i < p.nbins + 2; i += GEMM_THREADS)
+        for (int i = threadIdx.x; i < p.nbins + 2; i += ALL_T)
             s_table[i] = (EPI == EPI_VOTE) ? lut_pack(p.lut, i, p.nbins) : 0u;
     }
     tc_fence_before();
@@ -594,9 +623,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if constexpr (PAIR) cluster_sync_all();        // the peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    // where the consumers of this CTA hand queue slots / accumulator stages back: the leader's barriers
+    // where the consumers of this CTA hand queue slots back (the cluster leader's barriers) and accumulator
+    // stages back (their pair leader's)
     auto arrive_leader = [&](uint64_t* bar) {
         if constexpr (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(bar), 0u));
+        else mbar_arrive(bar);
+    };
+    auto arrive_pair_leader = [&](uint64_t* bar) {
+        if constexpr (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(bar), pair_lead));
         else mbar_arrive(bar);
     };
     auto wait_queue = [&](uint64_t* bar, uint32_t parity) {
@@ -625,9 +659,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     tile = (t < (unsigned int)p.total_tiles) ? (int)t : -1;
                     s_tileq[qs] = tile;
                     mbar_arrive(&qfull_bar[qs]);
-                    if constexpr (PAIR) {          // ... and into the peer CTA's copy of the queue
-                        st_remote_u32(mapa_u32(smem_u32(&s_tileq[qs]), 1u), (uint32_t)tile);
-                        mbar_arrive_remote(mapa_u32(smem_u32(&qfull_bar[qs]), 1u));
+                    if constexpr (PAIR) {          // ... and into the other CTAs' copies of the queue
+                        for (uint32_t r = 1; r < (uint32_t)CTAS; ++r) {
+                            st_remote_u32(mapa_u32(smem_u32(&s_tileq[qs]), r), (uint32_t)tile);
+                            mbar_arrive_remote(mapa_u32(smem_u32(&qfull_bar[qs]), r));
+                        }
                     }
                 } else {
                     wait_queue(&qfull_bar[qs], qph);
@@ -641,7 +677,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (tile < 0) break;
                 it.advance(tile - cur_tile);
                 cur_tile = tile;
-                const int m0 = it.mt * (BM * CTAS) + (int)cta_rank * BM, n0 = it.nt() * BN + (int)cta_rank * B_ROWS;
+                const int m0 = it.mt * (BM * CTAS) + (int)cta_rank * BM, n0 = it.nt() * BN + (int)pair_rank * B_ROWS;
                 for (int term = 0; term < p.n_terms; ++term) {
                     const CUtensorMap* ma = p.a_sel[term] ? &tm_a_lo : &tm_a_hi;
                     const CUtensorMap* mb = p.b_sel[term] ? &tm_b_lo : &tm_b_hi;
@@ -649,9 +685,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         unsigned char* sa = ring + (size_t)s * STAGE_BYTES;
                         if constexpr (PAIR) {
-                            if (leader) mbar_expect_tx(&full_bar[s], STAGE_BYTES * CTAS);
+                            if (pair_leader) mbar_expect_tx(&full_bar[s], STAGE_BYTES * 2);
                             tma_load_2d_pair(sa, ma, &full_bar[s], kb * BK, m0);
-                            tma_load_2d_pair(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                            if constexpr (QUAD) {      // pair 0 fetches the B half for its own CTA and the one below it
+                                if (cta_rank < 2u)
+                                    tma_load_2d_pair_mc(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0, (uint16_t)(5u << pair_rank));
+                            } else {
+                                tma_load_2d_pair(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                            }
                         } else {
                             mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                             tma_load_2d(sa, ma, &full_bar[s], kb * BK, m0);
@@ -667,14 +708,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && leader) {
-            const uint32_t idesc = make_idesc(BM * CTAS, BN);
+        if (lane == 0 && pair_leader) {
+            const uint32_t idesc = make_idesc(BM * (PAIR ? 2 : 1), BN);
+            const uint16_t pair_mask = (uint16_t)(3u << pair_lead);            // the two CTAs of this pair
+            const uint16_t slot_mask = QUAD ? (uint16_t)0xF : pair_mask;       // everyone whose producer reuses the slot
             int s = 0, a = 0, qs = 0;
             uint32_t ph = 0, aph = 0, qph = 0;
             for (;;) {
-                mbar_wait(&qfull_bar[qs], qph);
+                wait_queue(&qfull_bar[qs], qph);
                 const int tile = s_tileq[qs];
-                mbar_arrive(&qempty_bar[qs]);
+                arrive_leader(&qempty_bar[qs]);
                 if (++qs == TQ) {
                     qs = 0;
                     qph ^= 1u;
@@ -706,7 +749,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                        (i >= NCHAIN || k > 0) ? 1u : 0u);
                     }
                     // frees the smem slot (of both CTAs) once these MMAs retire
-                    if constexpr (PAIR) tc_commit_pair(&empty_bar[s]);
+                    if constexpr (PAIR) tc_commit_pair(&empty_bar[s], slot_mask);
                     else tc_commit(&empty_bar[s]);
                     if (++s == p.stages) {
                         s = 0;
@@ -714,7 +757,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     }
                 }
                 // accumulator complete -> epilogue (of both CTAs)
-                if constexpr (PAIR) tc_commit_pair(&tfull_bar[a]);
+                if constexpr (PAIR) tc_commit_pair(&tfull_bar[a], pair_mask);
                 else tc_commit(&tfull_bar[a]);
                 if (++a == ACC_STAGES) {
                     a = 0;
@@ -729,8 +772,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         const int half = ew >> 2;                     // which half of the tile's columns
         const int et = ew * 32 + lane;                // 0..255 among epilogue threads
         const int row_in_tile = q * 32 + lane;
-        constexpr int HALF_COLS = BN / 2;
-        const int cbeg = half * HALF_COLS;
+        constexpr int HALF_COLS = BN / (EW / 4);      // columns per warp: half of the tile (EW = 8) or a quarter (16)
+        const int cbeg = half * HALF_COLS;            // (half = ew >> 2 is the warp's column part, 0 .. EW/4 - 1)
         TileIter it;
         it.init(p, BN, 0);
         int cur_tile = 0;
@@ -753,8 +796,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const int64_t m0 = (int64_t)it.mt * (BM * CTAS) + (int64_t)cta_rank * BM, n0 = (int64_t)it.nt() * BN;
             const int64_t m = m0 + row_in_tile;
             // stage per-column metadata of this tile
-            epi_bar_sync();                           // previous tile's readers are done
-            for (int c = et; c < BN; c += EPI_THREADS) {
+            epi_bar_sync<EPI_T>();                           // previous tile's readers are done
+            for (int c = et; c < BN; c += EPI_T) {
                 const int64_t n = n0 + c;
                 const bool ok = n < p.N;
                 float ib = ok ? p.inv_b[n] : 0.f;
@@ -770,7 +813,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     if (lane == 0) s_flush[c >> 5] = msk;
                 }
             }
-            epi_bar_sync();
+            epi_bar_sync<EPI_T>();
             const bool row_ok = m < p.M;
             const float inv_i = row_ok ? p.inv_a[m] : 0.f;
 
@@ -778,8 +821,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)(a * ACC_COLS) + ((uint32_t)(q * 32) << 16);
             const int n_chains = n_iters < NCHAIN ? n_iters : NCHAIN;
-            // tile touches the diagonal: some column index <= some row index and vice versa
-            const bool diag_tile = (n0 <= m0 + BM - 1) && (n0 + BN - 1 >= m0);
+            // some column index <= some row index: the tile touches the diagonal or (the lower CTAs of a
+            // quad's first column tile) lies entirely below it -- either way the per-element test decides
+            const bool diag_tile = (n0 <= m0 + BM - 1);
 
             if (EPI == EPI_STORE) {
 #pragma unroll 1
@@ -805,8 +849,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 // (a pair's 256-row tile is stored as two 128-row tiles: 2 * tile + rank)
                 const int sp_tile = tile * CTAS + (int)cta_rank;
                 const bool do_spill = p.spill != nullptr && sp_tile < p.spill_tiles;
-                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)sp_tile * (size_t)(BM * BN)) +
-                            (size_t)(ew * (HALF_COLS / 32)) * 256 + lane;
+                const int sp_mode = p.dbg_skip_col >> 1;          // experiment switch MN_DBG_SPILL_MODE
+                const int sp_at = (sp_mode == 1) ? (sp_tile & 255) : sp_tile;
+                // the spill keeps the 8-warp layout [role][chunk]: role = (lane quarter, column half), BN/64 chunks
+                const int sp_role = ((q + 2) & 3) + 4 * (half / (EW / 8));
+                const int sp_chunk0 = (half % (EW / 8)) * (HALF_COLS / 32);
+                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)sp_at * (size_t)(BM * BN)) +
+                            (size_t)(sp_role * (BN / 64) + sp_chunk0) * 256 + lane;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
@@ -825,7 +874,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                     const int c = 4 * c4 + u;
                                     const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], half_bins, q_top);
                                     const bool use = ibv[u] > 0.f;
-                                    atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
+                                    if (!p.dbg_skip_col) atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
                                     r[c] = use ? qv : 0u;
                                 }
                             }
@@ -849,9 +898,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         for (int c = 0; c < 32; ++c) r[c] = 0u;
                     }
                     if (do_spill) {
+                        if (sp_mode == 2) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            __stcs(sp + k * 32, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+                            for (int k = 0; k < 8; ++k) sp[k * 32] = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+                        } else if (sp_mode == 3) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(sp + k * 32),
+                                             "r"(r[4 * k]), "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]), "l"(pol_ef) : "memory");
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                __stcs(sp + k * 32, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
+                        }
                         sp += 256;
                     }
                 }
@@ -902,20 +961,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             // the accumulator stage is drained: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) arrive_leader(&tempty_bar[a]);
+            if (lane == 0) arrive_pair_leader(&tempty_bar[a]);
             if (++a == ACC_STAGES) {
                 a = 0;
                 aph ^= 1u;
             }
 
             if (EPI == EPI_VOTE && p.tri != 0) {
-                epi_bar_sync();
+                epi_bar_sync<EPI_T>();
                 vote_merge_columns<BN>(s_colw, s_wlab, p.votes, n0, p.L, pol_ef, ew, lane, p.dbg_skip_col != 0);
             }
         }
         if (EPI == EPI_HIST) {
-            epi_bar_sync();
-            for (int b = et; b <= p.nbins; b += EPI_THREADS) {
+            epi_bar_sync<EPI_T>();
+            for (int b = et; b <= p.nbins; b += EPI_T) {
                 const uint32_t v = s_table[b];
                 if (v) atomicAdd(p.hist + (b < p.nbins ? b : p.nbins - 1), (unsigned long long)v);
             }
@@ -1229,8 +1288,19 @@ static int64_t corr_tile_count(int64_t N, int64_t row0, int64_t row1, int shard_
     return tiles;
 }
 
-// CTA pairs (cta_group::2) for the two network passes unless MN_GEMM_1CTA is set (debugging aid)
-static int corr_ctas(bool wide) { return (wide && !getenv("MN_GEMM_1CTA")) ? 2 : 1; }
+// CTAs per cluster for the two network passes: 2 (one cta_group::2 pair).  MN_GEMM_CTAS = 4 selects two pairs
+// sharing the B tile through TMA multicast, = 1 (or MN_GEMM_1CTA) single CTAs.  Measured at config 2 with the
+// board pinned at its 1,000 W cap in every variant (pass 1 is POWER-bound): pair 74.2 ms @ 1.44 GHz, pair
+// without spill 66.5 ms @ 1.53 GHz, single CTAs without spill 68.1 ms, quad 79.1 ms @ 1.55 GHz -- the quad
+// moves 25 % fewer operand bytes from L2 but its two pairs stall on each other's shared B slot.
+static int corr_ctas(bool wide) {
+    if (!wide || getenv("MN_GEMM_1CTA")) return 1;
+    if (const char* e = getenv("MN_GEMM_CTAS")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) return v;
+    }
+    return 2;
+}
 
 template <int BN>
 static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
@@ -1261,7 +1331,7 @@ static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <int BN, int EPI, int NCHAIN, int CTAS = 1>
+template <int BN, int EPI, int NCHAIN, int CTAS = 1, int EW = EPI_WARPS>
 static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, const __half* b_hi,
                        const __half* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -1269,8 +1339,9 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     int rc;
     if ((rc = make_map(&ta_hi, a_hi, M, cols_a, lda, BM))) return rc;
     if ((rc = make_map(&ta_lo, a_lo ? a_lo : a_hi, M, cols_a, lda, BM))) return rc;
-    if ((rc = make_map(&tb_hi, b_hi, N, cols_b, ldb, BN / CTAS))) return rc;
-    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, N, cols_b, ldb, BN / CTAS))) return rc;
+    constexpr int B_BOX = BN / (CTAS >= 2 ? 2 : 1);      // rows of B one CTA stages (half a tile in the pair forms)
+    if ((rc = make_map(&tb_hi, b_hi, N, cols_b, ldb, B_BOX))) return rc;
+    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, N, cols_b, ldb, B_BOX))) return rc;
     p.M = M;
     p.N = N;
     p.ctas = CTAS;
@@ -1278,9 +1349,9 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     p.k_last = (G - (p.k_blocks - 1) * BK + UMMA_K - 1) / UMMA_K;
     p.n_tiles = (int)((N + BN - 1) / BN);
     if (p.band <= 0) p.band = gemm_band() / CTAS;
-    const size_t stage_bytes = (size_t)(BM + BN / CTAS) * BK * 2;
+    const size_t stage_bytes = (size_t)(BM + B_BOX) * BK * 2;
     const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 2 + 3) & ~3) * 4;
-    const size_t fixed = table + (size_t)BN * 12 + (size_t)EPI_WARPS * (BN / 2) * 4 + EPI_WARPS * 4 +
+    const size_t fixed = table + (size_t)BN * 12 + (size_t)EW * (BN / 2) * 4 + EW * 4 +
                          (2 * MAX_STAGES + 4 + 2 * TQ) * 8 + TQ * 4 + 16;
     const size_t budget = 232448 - 1024;          // 227 KB minus alignment slack
     int stages = (int)((budget - fixed) / stage_bytes);
@@ -1295,7 +1366,7 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     }
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
-    auto kern = gemm_kernel<BN, EPI, NCHAIN, CTAS>;
+    auto kern = gemm_kernel<BN, EPI, NCHAIN, CTAS, EW>;
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // number of tiles (of BM * CTAS rows)
     long long tiles = 0;
@@ -1314,12 +1385,12 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     p.total_tiles = (int)tiles;
     MN_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), st));
     if (CTAS == 1) {
-        kern<<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+        kern<<<grid, 64 + EW * 32, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
     } else {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.blockDim = dim3(64 + EW * 32);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1411,6 +1482,8 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.inv_b = inv_norm;
     p.nbins = nbins;
     p.hist = reinterpret_cast<unsigned long long*>(hist);
+    p.dbg_skip_col = getenv("MN_DBG_NOHIST") ? 1 : 0;      // experiment switch: no histogram atomics (wrong results)
+    if (const char* e = getenv("MN_DBG_SPILL_MODE")) p.dbg_skip_col |= atoi(e) << 1;   // 1: wrap into 32 MB (wrong), 2: plain st, 3: evict-first hint
     MN_CHECK_ARG(spill_tiles >= 0 && (spill_tiles == 0 || spill != nullptr), "mn_corr_hist: spill_tiles without a spill buffer");
     MN_CHECK_ARG((reinterpret_cast<uintptr_t>(spill) & 15) == 0, "mn_corr_hist: spill must be 16-byte aligned");
     p.spill_tiles = (int)(spill_tiles > INT_MAX ? INT_MAX : spill_tiles) & ~(ctas - 1);    // whole pairs only
@@ -1420,6 +1493,10 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     // rows beyond row1 inside the last tile belong to the next shard: mask them via M
     // 128 x 256 tiles move 25 % fewer operand bytes per flop through L2 (the measured bound); the table
     // must then leave room for >= 2 pipeline stages of 48 KB, i.e. nbins <= 16384
+    if (wide && ctas == 4)
+        return launch_gemm<256, EPI_HIST, 1, 4>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    if (wide && ctas == 2 && getenv("MN_HIST_EW16"))     // 16 epilogue warps: measured no faster (73.0 vs 70.8 ms)
+        return launch_gemm<256, EPI_HIST, 1, 2, 16>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     if (wide && ctas == 2)
         return launch_gemm<256, EPI_HIST, 1, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     if (wide)
@@ -1501,7 +1578,9 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
         if (rc) return rc;
     }
     p.tile_base = (int)(n_sp / ctas);
-    if (wide && ctas == 2)
+    if (wide && ctas == 4)
+        rc = launch_gemm<256, EPI_VOTE, 1, 4>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
+    else if (wide && ctas == 2)
         rc = launch_gemm<256, EPI_VOTE, 1, 2>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);
     else if (wide)
         rc = launch_gemm<256, EPI_VOTE, 1>(h, l, ldd, row1, h, l, ldd, N, G, p, (cudaStream_t)stream);

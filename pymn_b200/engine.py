@@ -580,7 +580,8 @@ def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins
     perm, cell_label, seg_off = _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off)
     up.enqueue()                                 # the rest of the matrix follows the small arrays through the copy engine
     nd = max(1, min(STREAM_DEV_CHUNKS if STREAM_DEV_CHUNKS > 0 else STREAM_CHUNKS, N // 4096))
-    bounds = sorted(set([0, N] + [min(N, int(round(k * N / nd / 256.0)) * 256) for k in range(1, nd)]))
+    # (row chunks start on multiples of 512: the tile height of the widest GEMM form)
+    bounds = sorted(set([0, N] + [min(N, int(round(k * N / nd / 512.0)) * 512) for k in range(1, nd)]))
     nd = len(bounds) - 1
     # lowest input row that device rows >= b need
     suf_min = np.minimum.accumulate(perm_np[::-1])[::-1]
