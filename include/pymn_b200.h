@@ -155,7 +155,8 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
  * routes feed the same integers into the same weight map, so the vote sums are bit-identical for
  * any `spill_tiles`.  mn_corr_spill_layout reports the tile count and size of one shard: a buffer of
  * n_tiles * tile_bytes holds everything.  The same (N, row0, row1, shard, nbins) must be passed to
- * the layout query, mn_corr_hist and mn_corr_vote. */
+ * the layout query, mn_corr_hist and mn_corr_vote; row0 must be a multiple of 512 (the tallest tile of
+ * the GEMM forms).  spill_tiles is rounded down to whole cluster tiles (2 stored tiles per CTA pair). */
 int mn_corr_spill_layout(int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
                          int32_t nbins, int64_t* n_tiles /* host */, int64_t* tile_bytes /* host */);
 /* n_diag = number of diagonal entries (all cells, they tie at rho = 1 -- utils.py:72) */

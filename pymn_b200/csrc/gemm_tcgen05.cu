@@ -11,19 +11,24 @@
 // (hi*hi + hi*lo + lo*hi) are extra accumulation passes into the same TMEM
 // accumulator -- the fp16 analogue of a 3xTF32 split, but with exact limbs.
 //
-// Kernel anatomy (persistent, one CTA per SM, 320 threads):
-//   warp 0      TMA producer: claims tiles from a global atomic counter (dynamic scheduler), issues
-//               cp.async.bulk.tensor 2D tiles (128B swizzle) -> smem ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1,
-//               kind::f16, M=128, N=BN, K=16), tcgen05.commit -> mbarriers
+// Kernel anatomy (persistent, one CTA per SM, 320 threads; the two network passes run as CTA PAIRS --
+// clusters of two CTAs, tcgen05 cta_group::2, M = 256 -- see gemm_kernel):
+//   warp 0      TMA producer: the (cluster) leader claims tiles from a global atomic counter (dynamic
+//               scheduler) and publishes them to every role; cp.async.bulk.tensor 2D tiles
+//               (128B swizzle) -> smem ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M = 128 or 256, N = BN,
+//               K = 16), tcgen05.commit (multicast to both CTAs of a pair) -> mbarriers
 //   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns per warp; two warps per TMEM lane
 //               quarter, each half of the columns) from one of two TMEM accumulator stages while
 //               the next tile's MMAs run
 // Epilogues:
 //   EPI_STORE  votes_fast: scale + addend, store column-major FP32   (MetaNeighborUS.py:361-366)
-//   EPI_HIST   pass 1 of the global rank: rho -> shared-memory histogram (utils.py:44-45)
-//   EPI_VOTE   pass 2: rho -> W via CDF LUT -> integer per-label vote sums + node degree
-//              (utils.py:46-51 + MetaNeighborUS.py:165-169); the N x N network never exists.
+//   EPI_HIST   pass 1 of the global rank: rho -> shared-memory histogram (utils.py:44-45), and the
+//              16.16 fixed-point bin position of every pair -> the rho spill in HBM
+//   EPI_VOTE   pass 2 for tiles that were not spilled: rho -> W via CDF LUT -> integer per-label vote
+//              sums + node degree (utils.py:46-51 + MetaNeighborUS.py:165-169)
+// vote_spill_kernel is pass 2 for the spilled tiles: it streams the bin positions back from HBM.
+// The float64 N x N network of the reference never exists.
 #include <cuda.h>
 #include <stdlib.h>
 
