@@ -76,6 +76,10 @@ auroc_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, const floa
     __shared__ unsigned int hist[4][256];
     __shared__ unsigned int wcnt[ANW][256];
     __shared__ unsigned int base[256];
+    __shared__ unsigned int tcount[256], tstart[256];      // this tile's keys per digit / their start inside the tile
+    __shared__ unsigned int s_scan[8];
+    __shared__ uint32_t s_key[ATILE];                      // the tile in digit order, staged for coalesced write-out
+    __shared__ uint16_t s_lab[ATILE];
     __shared__ int s_warp[32];
     __shared__ int s_flag[4];
 
@@ -254,27 +258,57 @@ auroc_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, const floa
                 __syncwarp();
             }
             __syncthreads();
+            // Scatter through shared memory: a key's 4-byte store to its bucket is a whole 32-byte sector write
+            // for L2, and with 256 buckets almost every store of a tile hits a different sector.  Instead the
+            // tile is first put into digit order in shared memory; consecutive threads then write consecutive
+            // elements of a digit's run to consecutive global addresses.
+            unsigned incl = 0;
             if (tid < 256) {
-                unsigned run = base[tid];
+                unsigned run = 0;
 #pragma unroll
                 for (int w = 0; w < ANW; ++w) {
                     const unsigned c = wcnt[w][tid];
-                    wcnt[w][tid] = run;
+                    wcnt[w][tid] = run;                    // offset of warp w's keys inside digit tid's run of this tile
                     run += c;
                 }
-                base[tid] = run;
+                tcount[tid] = run;
+                incl = run;                                 // inclusive scan over the 256 digits -> start of each run
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) s_scan[warp] = incl;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                unsigned before = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    if (w < warp) before += s_scan[w];
+                tstart[tid] = before + incl - tcount[tid];
             }
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < AITEMS; ++j) {
                 if (off[j] >= 0) {
                     const unsigned dig = (key[j] >> shift) & 255u;
-                    const unsigned pos = wc[dig] + (unsigned)off[j];
-                    kdst[pos] = key[j];
-                    ldst[pos] = lab[j];
+                    const unsigned lpos = tstart[dig] + wc[dig] + (unsigned)off[j];
+                    s_key[lpos] = key[j];
+                    s_lab[lpos] = lab[j];
                 }
             }
             __syncthreads();
+            const int tile_n = min(ATILE, n - t0);
+            for (int i = tid; i < tile_n; i += AT) {
+                const uint32_t k = s_key[i];
+                const unsigned dig = (k >> shift) & 255u;
+                const unsigned pos = base[dig] + ((unsigned)i - tstart[dig]);
+                kdst[pos] = k;
+                ldst[pos] = s_lab[i];
+            }
+            __syncthreads();
+            if (tid < 256) base[tid] += tcount[tid];
         }
         cur = nxt;
         __threadfence_block();
@@ -511,7 +545,8 @@ int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom,
                                    n_pos, keys0, keys1, labs0, labs1, st);
     const size_t dyn = (size_t)n_labels * 12 + 16;
     static size_t configured = 0;
-    if (dyn > 16 * 1024 && dyn > configured) {
+    // (the kernel's static shared memory is already ~47 KB: any dynamic part needs the opt-in)
+    if (dyn > configured) {
         MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured = dyn;
     }
