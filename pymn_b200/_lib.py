@@ -14,7 +14,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpymn_b200.so")
+LIB_PATH = os.environ.get("PYMN_B200_LIB") or os.path.join(_HERE, "libpymn_b200.so")   # (override: tuning builds)
 
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
 

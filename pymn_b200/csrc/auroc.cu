@@ -16,10 +16,10 @@
 
 namespace mn {
 
-constexpr int AT = 512;                 // threads per CTA
-constexpr int ANW = AT / 32;            // warps
-constexpr int AITEMS = 8;               // keys per thread per tile
-constexpr int ATILE = AT * AITEMS;      // keys per tile
+// The sort kernel is instantiated for 512 and 256 threads per CTA (8 keys per thread per tile): many
+// (column, study) segments (config 4: 7,350 of 71k cells) run faster with more, smaller CTAs per SM, few
+// long segments (config 5: 150 of 1M cells; config 2: 160 of 50k) with more threads per segment
+// (measured on one box: c4 47.9 vs 40.9 ms, c5 28.7 vs 42.9 ms, c1 0.18 vs 0.21 ms for 512 vs 256).
 
 __device__ __forceinline__ float vote_value(const float* __restrict__ v, const float* __restrict__ dn, int64_t i) {
     const float x = v[i];
@@ -27,6 +27,7 @@ __device__ __forceinline__ float vote_value(const float* __restrict__ v, const f
 }
 
 // inclusive max-scan over the block; returns the scanned value, *total = block max.
+template <int ANW>
 __device__ __forceinline__ int block_scan_max(int v, int* s_warp, int* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -62,11 +63,15 @@ __global__ void fill_f64_kernel(double* p, int64_t n, double val) {
     if (i < n) p[i] = val;
 }
 
+template <int AT, int AITEMS>
 __global__ void __launch_bounds__(AT)
 auroc_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, const float* __restrict__ denom,
              const int32_t* __restrict__ col_denom, const int32_t* __restrict__ seg_off,
              const int32_t* __restrict__ cell_label, int n_labels, int64_t M, double* __restrict__ auroc,
              int32_t* __restrict__ n_pos_out, uint32_t* keys0, uint32_t* keys1, uint16_t* labs0, uint16_t* labs1) {
+    constexpr int ANW = AT / 32;            // warps
+    constexpr int ATILE = AT * AITEMS;      // keys per tile
+    static_assert(AT >= 256, "256 threads own the 256 digits");
     extern __shared__ __align__(16) unsigned char dyn[];
     // per-label sum of 2*rank as a (lo, hi) pair of 32-bit words: native 32-bit shared
     // atomics with an explicit carry instead of a 64-bit CAS loop
@@ -544,15 +549,30 @@ int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom,
         return mn::launch_auroc_ss(votes, ldv, ncols, denom, col_denom, seg_off, n_seg, cell_label, n_labels, per, auroc,
                                    n_pos, keys0, keys1, labs0, labs1, st);
     const size_t dyn = (size_t)n_labels * 12 + 16;
-    static size_t configured = 0;
-    // (the kernel's static shared memory is already ~47 KB: any dynamic part needs the opt-in)
-    if (dyn > configured) {
-        MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        configured = dyn;
-    }
     dim3 grid((unsigned)ncols, (unsigned)n_seg);
-    mn::auroc_kernel<<<grid, mn::AT, dyn, st>>>(votes, ldv, ncols, denom, col_denom, seg_off, cell_label, n_labels,
-                                               per, auroc, n_pos, keys0, keys1, labs0, labs1);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // many segments -> 256-thread CTAs (more of them per SM); few -> 512 threads per segment
+    bool small_cta = (int64_t)ncols * n_seg >= 8ll * sms;
+    if (const char* e = getenv("MN_AUROC_AT")) small_cta = atoi(e) == 256;      // tuning knob
+    // (the kernels' static shared memory is ~28-47 KB: any dynamic part needs the opt-in)
+    static size_t configured[2] = {0, 0};
+    if (small_cta) {
+        if (dyn > configured[0]) {
+            MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured[0] = dyn;
+        }
+        mn::auroc_kernel<256, 8><<<grid, 256, dyn, st>>>(votes, ldv, ncols, denom, col_denom, seg_off, cell_label, n_labels,
+                                                        per, auroc, n_pos, keys0, keys1, labs0, labs1);
+    } else {
+        if (dyn > configured[1]) {
+            MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured[1] = dyn;
+        }
+        mn::auroc_kernel<512, 8><<<grid, 512, dyn, st>>>(votes, ldv, ncols, denom, col_denom, seg_off, cell_label, n_labels,
+                                                        per, auroc, n_pos, keys0, keys1, labs0, labs1);
+    }
     MN_LAUNCH_CHECK();
     return 0;
 }
