@@ -1315,7 +1315,9 @@ static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
         if (v >= 4 && v <= SPILL_WARPS && (v & 3) == 0) warps = v;
     }
     // per warp a 4 KB slot, its mbarrier and its column sums (8 chunks x 32 lanes x 8 B), then the packed LUT
-    const size_t smem = (size_t)warps * (4096 + 8 + (BN / 32) * 32 * 8) + (size_t)((p.nbins + 2 + 3) & ~3) * 4;
+    const size_t per_warp = 4096 + 8 + (size_t)(BN / 32) * 32 * 8, table = (size_t)((p.nbins + 2 + 3) & ~3) * 4;
+    while (warps > 4 && warps * per_warp + table > 232448) warps -= 4;        // 32,768 bins leave room for 16 warps
+    const size_t smem = (size_t)warps * per_warp + table;
     // (the register budget per thread follows the warp count: 24 warps -> 80, 20 -> 96, 16 -> 128)
     auto kern = warps > 20 ? vote_spill_kernel<BN, 24> : (warps > 16 ? vote_spill_kernel<BN, 20> : vote_spill_kernel<BN, 16>);
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -272,3 +272,36 @@ def test_corr_hist_and_votes(eng, n, g):
         v2, d2, h2, _ = eng.corr_network_votes(rc, eng._i32(label), L, nbins=nb, spill_tiles=tiles)
         torch.cuda.synchronize()
         assert torch.equal(h2, hist) and torch.equal(v2, votes) and torch.equal(d2, degree), f"spill_tiles={tiles}"
+
+
+def test_corr_gemm_forms_identical(eng, monkeypatch):
+    """Single CTAs, CTA pairs (default) and quad clusters (two pairs, B tile TMA-multicast) are three
+    schedules of the same arithmetic: histogram, LUT and vote sums must be bit-identical -- with and
+    without the rho spill.  Also the 128-column tile form selected by nbins > 16384."""
+    make_counts = __import__("pymn_b200.synth", fromlist=["make_counts"]).make_counts
+    x, s, c = make_counts(99, 2, 900, 200, 4)
+    x[11] = 0
+    rc = eng.rank_normalize(eng.to_device(x))
+    rng = np.random.default_rng(5)
+    L = 6
+    label = np.sort(rng.integers(0, L, size=x.shape[0])).astype(np.int32)
+    ref = eng.corr_network_votes(rc, eng._i32(label), L, nbins=8192)
+    torch.cuda.synchronize()
+    for ctas in ("1", "4"):
+        monkeypatch.setenv("MN_GEMM_CTAS", ctas)
+        for tiles in (None, 0, 5):
+            got = eng.corr_network_votes(rc, eng._i32(label), L, nbins=8192, spill_tiles=tiles)
+            torch.cuda.synchronize()
+            for a, b, what in zip(got, ref, ("votes", "degree", "hist", "lut")):
+                assert torch.equal(a, b), f"ctas={ctas} spill_tiles={tiles}: {what} differs"
+    monkeypatch.delenv("MN_GEMM_CTAS")
+    # 32768 bins: 128 x 128 tiles, single CTAs; self-consistency across the spill settings
+    big = eng.corr_network_votes(rc, eng._i32(label), L, nbins=32768)
+    torch.cuda.synchronize()
+    m = int((rc.inv_norm > 0).sum().item())
+    assert int(big[2].sum().item()) == m * (m - 1) // 2
+    assert torch.equal(big[0].sum(dim=1), big[1])
+    for tiles in (0, 3):
+        got = eng.corr_network_votes(rc, eng._i32(label), L, nbins=32768, spill_tiles=tiles)
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], big[0]) and torch.equal(got[1], big[1]) and torch.equal(got[2], big[2])
