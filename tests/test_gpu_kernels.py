@@ -305,3 +305,41 @@ def test_corr_gemm_forms_identical(eng, monkeypatch):
         got = eng.corr_network_votes(rc, eng._i32(label), L, nbins=32768, spill_tiles=tiles)
         torch.cuda.synchronize()
         assert torch.equal(got[0], big[0]) and torch.equal(got[1], big[1]) and torch.equal(got[2], big[2])
+
+
+def test_corr_votes_heavy_ties_wide_lut(eng):
+    """Six genes: rho takes a handful of values, single bins hold far more than 0.2 % of all pairs, so the
+    packed LUT's 11-bit rise field overflows and pass 2 must take its two-load form (lut[nbins + 1] == 1).
+    Vote sums still equal the host evaluation of the same LUT and do not depend on the spill."""
+    rng = np.random.default_rng(17)
+    n, g, L, nb = 900, 6, 4, 4096
+    x = rng.poisson(1.0, size=(n, g)).astype(np.float32)
+    rc = eng.rank_normalize(eng.to_device(x))
+    label = np.sort(rng.integers(0, L, size=n)).astype(np.int32)
+    votes, degree, hist, lut = eng.corr_network_votes(rc, eng._i32(label), L, nbins=nb)
+    torch.cuda.synchronize()
+    lut_h = lut.cpu().numpy().astype(np.int64)
+    assert lut_h[nb + 1] == 1, "this case is meant to exercise the wide LUT form"
+    d = _planes(rc, g)
+    inv = rc.inv_norm.cpu().numpy()
+    kept = inv > 0
+    acc = (d @ d.T).astype(np.float32)
+    pos = np.float32(0.5 * nb)
+    t = (acc * (inv[:, None] * pos)).astype(np.float32)
+    binpos = (t.astype(np.float64) * inv[None, :].astype(np.float64) + np.float64(pos)).astype(np.float32)
+    q = np.minimum(np.floor(np.clip(binpos, 0, None).astype(np.float64) * 65536.0).astype(np.int64), nb << 16)
+    qb = q >> 16
+    lut_p = np.append(lut_h[:nb + 1], lut_h[nb])
+    w = lut_p[qb] + (((lut_p[qb + 1] - lut_p[qb]) * (q & 0xffff)) >> 16)
+    w[~kept, :] = 0
+    w[:, ~kept] = 0
+    np.fill_diagonal(w, 0)
+    # (equal up to a last-bit difference of an fmaf emulated in float64: one unit of q moves a weight by rise / 65536)
+    ref_deg = w.sum(axis=1)
+    ref_votes = np.stack([w[:, label == l].sum(axis=1) for l in range(L)], axis=1)
+    assert np.abs(degree.cpu().numpy() - ref_deg).max() <= 1e-6 * ref_deg.max()
+    assert np.abs(votes.cpu().numpy() - ref_votes).max() <= 1e-6 * ref_votes.max()
+    assert torch.equal(votes.sum(dim=1), degree)
+    v0, d0, h0, _ = eng.corr_network_votes(rc, eng._i32(label), L, nbins=nb, spill_tiles=0)
+    torch.cuda.synchronize()
+    assert torch.equal(v0, votes) and torch.equal(d0, degree) and torch.equal(h0, hist)
