@@ -104,13 +104,22 @@ def MetaNeighbor(
     gs_values = genesets.values
     n_sets = gs_values.shape[1]
     mine = shard_columns(n_sets, rank, world)
-    Xd, perm_dev = engine.supervised_prepare(expression, lay)
+    ctx = engine.supervised_prepare(expression, lay)
+    # the gene columns of all of this rank's sets go up in one copy; the per-set tables stay on the device
+    # until the end, so the host enqueues set j + 1 while the GPU still works on set j
+    col_lists = [np.flatnonzero(gs_values[:, j]).astype(np.int32) for j in mine]
+    offs = np.concatenate([[0], np.cumsum([len(c) for c in col_lists])]).astype(np.int64)
+    all_cols = engine._i32(np.concatenate(col_lists) if col_lists else np.zeros(0, np.int32))
+    tables = []
+    for jj in range(len(mine)):
+        tables.append(engine.supervised_geneset(ctx, all_cols[offs[jj]:offs[jj + 1]], K,
+                                                bool(node_degree_normalization), bool(fast_version)))
     local = np.full((K, len(mine)), np.nan)
-    for jj, j in enumerate(mine):
-        cols = np.flatnonzero(gs_values[:, j]).astype(np.int32)
-        auc = engine.supervised_geneset(Xd, perm_dev, cols, lay, K, bool(node_degree_normalization),
-                                        bool(fast_version))
-        local[:, jj] = _reduce_over_studies(auc.cpu().numpy(), S, K)
+    if tables:
+        import torch
+        stacked = torch.stack(tables).cpu().numpy()              # one device -> host copy
+        for jj in range(len(mine)):
+            local[:, jj] = _reduce_over_studies(stacked[jj], S, K)
     table = gather_columns(local, n_sets, rank, world)
     results = pd.DataFrame(table, index=ct_names, columns=genesets.columns)
     if save_uns:

@@ -685,25 +685,41 @@ def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):
 
 
 # ---- supervised ------------------------------------------------------------
-def supervised_prepare(X, lay: LabelLayout):
-    """Upload the shared expression matrix once (MetaNeighbor.py:80-83)."""
-    return to_device(X, torch.float32), _i32(lay.perm)
+@dataclass
+class SupervisedContext:
+    """Everything the per-gene-set pipeline needs that does not depend on the gene set, resident in HBM:
+    the expression matrix and the label arrays (uploading them again for every set costs four
+    synchronous pageable copies per set)."""
+    Xd: torch.Tensor
+    perm: torch.Tensor
+    cell_label: torch.Tensor
+    cell_study: torch.Tensor
+    lab_row_off: torch.Tensor
+    seg_off: torch.Tensor
+    n_studies: int
 
 
-def supervised_geneset(Xd, perm_dev, cols: np.ndarray, lay: LabelLayout, n_types: int, ndn=True, fast=False,
+def supervised_prepare(X, lay: LabelLayout) -> SupervisedContext:
+    """Upload the shared expression matrix and the label layout once (MetaNeighbor.py:80-83)."""
+    return SupervisedContext(to_device(X, torch.float32), _i32(lay.perm), _i32(lay.cell_label), _i32(lay.cell_study),
+                             _i32(lay.lab_row_off), _i32(lay.seg_off), len(lay.studies))
+
+
+def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types: int, ndn=True, fast=False,
                        nbins=DEFAULT_NBINS):
-    """One gene set.  ``lay`` is the layout of JOINT labels study*K + type (all S*K ids,
-    empty ranges allowed).  Returns float64 [S*K, K] AUROC table (rows = joint test labels)."""
-    S = len(lay.studies)
+    """One gene set.  ``col_index``: int32 device tensor of the set's gene columns.  The layout behind ``ctx``
+    is that of JOINT labels study*K + type (all S*K ids, empty ranges allowed).  Returns the float64
+    [S*K, K] AUROC table (rows = joint test labels) ON THE DEVICE: nothing here synchronises, so the
+    caller can keep enqueuing gene sets and fetch all tables with one copy."""
+    S = ctx.n_studies
     K = n_types
-    col_index = _i32(cols)
-    rc = rank_normalize(Xd, row_index=perm_dev, col_index=col_index, drop_mode=1 if fast else 0)
+    Xd = ctx.Xd
+    rc = rank_normalize(Xd, row_index=ctx.perm, col_index=col_index, drop_mode=1 if fast else 0)
     dev = Xd.device
-    cell_label = _i32(lay.cell_label)
-    cell_study = _i32(lay.cell_study)
+    cell_label, cell_study = ctx.cell_label, ctx.cell_study
     vmat = torch.empty((K, rc.M), dtype=torch.float32, device=dev)
     if fast:
-        C, n_valid = centroids(rc, _i32(lay.lab_row_off), S * K)
+        C, n_valid = centroids(rc, ctx.lab_row_off, S * K)
         b_hi, b_lo, inv_scale = split_f16(C, rc.G)
         out = votes_fast(rc, b_hi, b_lo, inv_scale, None, S * K)
         _lib.call("mn_loso_finalize", out, rc.M, 0, None, n_valid, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
@@ -713,5 +729,5 @@ def supervised_geneset(Xd, perm_dev, cols: np.ndarray, lay: LabelLayout, n_types
         votes, degree, _, _ = corr_network_votes(rc, cell_label, S * K, nbins)
         _lib.call("mn_loso_finalize", votes, S * K, 1, degree, None, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
         test_label = cell_label
-    auc, _ = auroc(vmat, K, None, None, _i32(lay.seg_off), S, test_label, S * K)
+    auc, _ = auroc(vmat, K, None, None, ctx.seg_off, S, test_label, S * K)
     return auc
