@@ -231,7 +231,8 @@ def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_tr
     cols = torch.arange(rank, n_train, world, device=dev) if world > 1 else None
     n_loc = int(cols.numel()) if cols is not None else n_train
     kept = rc.inv_norm > 0
-    cell_label = torch.where(kept, _i32(lay.cell_label), torch.full_like(_i32(lay.cell_label), -1))
+    cell_label_all = _i32(lay.cell_label)
+    cell_label = torch.where(kept, cell_label_all, torch.full_like(cell_label_all, -1))
     seg_off = _i32(lay.seg_off)
     if cols is not None:
         rows = torch.cat([cols, torch.arange(n_train, n_train + n_train_studies, device=dev)])
