@@ -34,7 +34,7 @@ def metaNeighborUS_fast(X, S, C, node_degree_normalization, one_vs_best, compute
     """MetaNeighborUS.py:228-306.  S, C: pandas Series (or arrays) of labels."""
     S = S.values if hasattr(S, "values") else np.asarray(S)
     C = C.values if hasattr(C, "values") else np.asarray(C)
-    Xd = engine.to_device_matrix(prepare_matrix(X))     # the upload runs while the host encodes the labels
+    Xd = engine.start_upload(prepare_matrix(X))         # the upload runs while the host encodes the labels
     lay = label_layout(S, C)
     r = engine.us_fast(Xd, lay, bool(node_degree_normalization), bool(one_vs_best))
     keep = _keep_rows(r["n_pos"])        # labels whose cells were all zero-variance vanish (:273-281)
@@ -54,7 +54,7 @@ def MetaNeighborUS_from_trained(trained_model, test_data, study_col, ct_col, nod
     """MetaNeighborUS.py:391-430."""
     S = np.asarray(study_col, dtype=object)
     C = np.asarray(ct_col, dtype=object)
-    Xd = engine.to_device_matrix(prepare_matrix(test_data))     # the upload runs while the host encodes the labels
+    Xd = engine.start_upload(prepare_matrix(test_data))         # the upload runs while the host encodes the labels
     lay = label_layout(S, C, replace_bar=True)
     cols = trained_model.columns
     cent = np.ascontiguousarray(trained_model.iloc[1:].values.T, dtype=np.float32)      # [L_train, G]

@@ -281,12 +281,21 @@ def _allreduce_max(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def ranked_cells(X, lay: LabelLayout, drop_mode=0) -> RankedCells:
+    """K1 over all cells, in label-sorted order, however the matrix arrives: host / device array or CSR
+    (upload, then rank), an AsyncUpload (wait for the chunks), or a ShardedUpload (multi-GPU: rank the own
+    slice, all-gather the planes)."""
+    if isinstance(X, ShardedUpload):
+        return ranked_cells_sharded(X, lay, drop_mode)
+    Xd = X.wait_all() if isinstance(X, AsyncUpload) else to_device_matrix(X)
+    return rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=drop_mode)
+
+
 def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
-    """metaNeighborUS_fast.  X: numpy / torch float32 [N, G] (input cell order).
-    Returns dict(table [L, L] rows = test labels, cols = train labels (both row order),
+    """metaNeighborUS_fast.  X: numpy / torch float32 [N, G] (input cell order), CSR, or an upload in flight
+    (start_upload).  Returns dict(table [L, L] rows = test labels, cols = train labels (both row order),
     auroc (one-vs-rest table), n_pos [L], flags uint8 [N] in device row order)."""
-    Xd = to_device_matrix(X)
-    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
+    rc = ranked_cells(X, lay, 0)
     L, S = len(lay.row_labels), len(lay.studies)
     C, n_valid = centroids(rc, _i32(lay.lab_row_off), L, extra_rows=S)
     train_study = _i32(lay.label_study)
@@ -301,8 +310,7 @@ def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.
                   n_model_studies: int, ndn=True, ovb=False):
     """MetaNeighborUS_from_trained.  model_centroids float [L_train, G] (rows = model
     columns), model_n [L_train], model_study int [L_train]."""
-    Xd = to_device_matrix(X)
-    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=0)
+    rc = ranked_cells(X, lay, 0)
     Lt = int(model_centroids.shape[0])
     C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)
     C[:Lt, :rc.G] = to_device(np.asarray(model_centroids, np.float32))
@@ -318,8 +326,7 @@ def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.
 
 def train_model(X, lay: LabelLayout):
     """trainModel: returns dict(centroids float32 [L, G], n_cells [L], flags [N] device row order)."""
-    Xd = to_device_matrix(X)
-    rc = rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=1)
+    rc = ranked_cells(X, lay, 1)
     L = len(lay.row_labels)
     C, n_valid = centroids(rc, _i32(lay.lab_row_off), L)
     return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=rc.flags.cpu().numpy())
@@ -648,24 +655,28 @@ class ShardedUpload:
         self.rank, self.world, self.per = rank, world, per
 
 
-def us_default_sharded(sh: ShardedUpload, lay: LabelLayout, L, S, ndn=True, nbins=DEFAULT_NBINS):
-    """Full-network pipeline with data-parallel ingestion: every rank ranks the cells of its own
-    input slice (K1, input order), one NCCL all-gather makes the fp16 planes (0.8 GB at config 2, ~ms over
-    NVLink instead of N x the matrix over PCIe) and scales available everywhere, a row gather puts them
-    into label-sorted order, and the passes run sharded by row tile as before.  K1 is row-wise, so the
-    planes -- and therefore the tables -- are identical to the single-GPU ones."""
-    rank, world, reduce_fn = dist_shard()
+def ranked_cells_sharded(sh: ShardedUpload, lay: LabelLayout, drop_mode=0) -> RankedCells:
+    """Data-parallel ingestion: every rank ranks the cells of its own input slice (K1, input
+    order), one NCCL all-gather makes the fp16 planes (0.8 GB at config 2, ~ms over NVLink instead of N x
+    the matrix over PCIe) and scales available everywhere, and a row gather puts them into label-sorted
+    order.  K1 is row-wise, so the planes are identical to the single-GPU ones."""
+    _rank, world, _ = dist_shard()
     N, G = sh.shape
     per = sh.per
-    rc_loc = rank_normalize(sh.X_local, drop_mode=0)
+    rc_loc = rank_normalize(sh.X_local, drop_mode=drop_mode)
     perm = to_device(np.asarray(lay.perm, dtype=np.int64))
     d_hi = gather_rows(rc_loc.d_hi, per, world).index_select(0, perm)
     d_lo = gather_rows(rc_loc.d_lo, per, world).index_select(0, perm) if rc_loc.d_lo is not None else None
     inv_norm = gather_rows(rc_loc.inv_norm, per, world).index_select(0, perm)
     flags = gather_rows(rc_loc.flags, per, world).index_select(0, perm)
-    rc = RankedCells(d_hi, d_lo, rc_loc.ldd, inv_norm, flags, N, G)
-    return network_from_ranked(rc, _i32(lay.cell_label), _i32(lay.seg_off), L, S, ndn, nbins,
-                               (rank, world, reduce_fn))
+    return RankedCells(d_hi, d_lo, rc_loc.ldd, inv_norm, flags, N, G)
+
+
+def us_default_sharded(sh: ShardedUpload, lay: LabelLayout, L, S, ndn=True, nbins=DEFAULT_NBINS):
+    """Full-network pipeline with data-parallel ingestion: ranked_cells_sharded, then the passes sharded by
+    row tile as before; the tables are identical to the single-GPU ones."""
+    rc = ranked_cells_sharded(sh, lay, 0)
+    return network_from_ranked(rc, _i32(lay.cell_label), _i32(lay.seg_off), L, S, ndn, nbins, dist_shard())
 
 
 def us_default(X, lay: LabelLayout, ndn=True, nbins=DEFAULT_NBINS):

@@ -26,7 +26,7 @@ def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
     assert var_genes.shape[0] > 2, "Must have at least 2 genes"
 
     sub = adata[:, var_genes]
-    X = engine.to_device_matrix(prepare_matrix(sub.X))   # the upload runs while the host encodes the labels
+    X = engine.start_upload(prepare_matrix(sub.X))       # the upload runs while the host encodes the labels
     S = np.asarray(sub.obs[study_col].values, dtype=object)
     C = np.asarray(sub.obs[ct_col].values, dtype=object)
     lay = label_layout(S, C)

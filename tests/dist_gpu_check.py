@@ -43,6 +43,15 @@ def main():
     finally:
         engine.dist_shard = saved_shard
     assert np.array_equal(api_multi.values, api_single.values, equal_nan=True), "sharded-ingestion table differs"
+    for ovb in (False, True):                      # ... and the centroid path through the API (sharded ingestion too)
+        kwf = dict(fast_version=True, one_vs_best=ovb, symmetric_output=False, save_uns=False)
+        f_multi = pymn_b200.MetaNeighborUS(make_adata(inp0), "study_id", "cell_type", **kwf)
+        engine.dist_shard = lambda: (0, 1, None)
+        try:
+            f_single = pymn_b200.MetaNeighborUS(make_adata(inp0), "study_id", "cell_type", **kwf)
+        finally:
+            engine.dist_shard = saved_shard
+        assert np.array_equal(f_multi.values, f_single.values, equal_nan=True), f"fast API table differs (ovb={ovb})"
 
     # centroid (fast) path: train columns are dealt to the ranks, tables all-gathered
     for ovb in (False, True):
