@@ -125,6 +125,41 @@ def main():
                 extra = f"  {2.0 * N * G * (n_train + 3) / v / 1e9:8.1f} TFLOP/s"
             print(f"   {k:22s} {v:9.3f} ms{extra}")
         print("   auroc finite:", bool(torch.isfinite(auc).all().item()), " mean:", float(auc.mean().item()))
+    if "--e2e" in sys.argv and not pretrained:
+        # end to end through the public API: pinned host matrix -> pymn_b200.MetaNeighborUS -> host table
+        # (label encoding, upload -- each rank only its slice of the cells on N > 1 GPUs --, kernels, D2H)
+        import pandas as pd
+        import pymn_b200
+        from pymn_b200.anndata_lite import AnnDataLite
+        Xh = torch.empty(tuple(Xd.shape), dtype=torch.float32, pin_memory=True)
+        Xh.copy_(Xd)
+        torch.cuda.synchronize()
+        var = pd.DataFrame({"highly_variable": np.ones(G, bool)}, index=pd.Index([f"g{i}" for i in range(G)], dtype=object))
+
+        class _AllGenes(AnnDataLite):
+            def __getitem__(self, key):          # the identity gene selection would copy the host matrix
+                return self
+        ad = _AllGenes(Xh.numpy(), pd.DataFrame({"study_id": s, "cell_type": c}), var)
+
+        def call():
+            t = pymn_b200.MetaNeighborUS(ad, "study_id", "cell_type", fast_version=True, one_vs_best=ovb,
+                                         symmetric_output=False, save_uns=False)
+            torch.cuda.synchronize()
+            return t
+        call()
+        if world > 1:
+            dist.barrier()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            call()
+            ts.append(time.perf_counter() - t0)
+        te = torch.tensor([float(np.median(ts))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"   e2e through pymn_b200.MetaNeighborUS (pinned host matrix, {Xh.numel() * 4 / 1e9:.1f} GB): "
+                  f"{float(te.item()) * 1e3:.0f} ms per call on {world} GPU(s)")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
