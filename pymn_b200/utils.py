@@ -87,10 +87,23 @@ class LabelLayout:
     sorted_pos: np.ndarray
 
 
+def _factorize_two(a, b):
+    """The two obs columns are factorised side by side (the Arrow / pandas hash kernels release the GIL)."""
+    n = len(a)
+    if n < 100_000:
+        return _factorize_sorted(a), _factorize_sorted(b)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        fa, fb = ex.submit(_factorize_sorted, a), ex.submit(_factorize_sorted, b)
+        return fa.result(), fb.result()
+
+
 def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
-    st_uniq, st_codes = _factorize_sorted(study)
-    ct_uniq, ct_codes = _factorize_sorted(ctype)
+    (st_uniq, st_codes), (ct_uniq, ct_codes) = _factorize_two(study, ctype)
     n_ct = len(ct_uniq)
+    # (32-bit codes when they fit: the O(N) passes below are memory-bound on the host)
+    if len(st_uniq) * n_ct < (1 << 31):
+        st_codes, ct_codes = st_codes.astype(np.int32), ct_codes.astype(np.int32)
     pair = st_codes * n_ct + ct_codes
     # distinct (study, type) pairs, ascending, and each cell's index into them (O(N): the code space is small)
     n_codes = len(st_uniq) * n_ct
@@ -109,8 +122,8 @@ def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     # row order: study (sorted) major, joined label (sorted as a string) minor
     order = sorted(range(len(names)), key=lambda i: (int(st_of[i]), names[i]))
     order = np.asarray(order, dtype=np.int64)
-    rank_of_pair = np.empty(len(names), np.int64)
-    rank_of_pair[order] = np.arange(len(names))
+    rank_of_pair = np.empty(len(names), np.int32)
+    rank_of_pair[order] = np.arange(len(names), dtype=np.int32)
     cell_label = rank_of_pair[pair_codes]
     perm = _stable_argsort_small(cell_label, len(names))
     row_labels = names[order]
@@ -124,9 +137,10 @@ def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     glob = sorted(range(n_lab), key=lambda i: row_labels[i])
     sorted_pos = np.empty(n_lab, np.int64)
     sorted_pos[np.asarray(glob, dtype=np.int64)] = np.arange(n_lab)
+    cell_label_sorted = cell_label[perm].astype(np.int32)
     return LabelLayout(studies=st_uniq, row_labels=row_labels, perm=perm.astype(np.int32),
-                       cell_label=cell_label[perm].astype(np.int32),
-                       cell_study=label_study[cell_label[perm]].astype(np.int32),
+                       cell_label=cell_label_sorted,
+                       cell_study=label_study[cell_label_sorted].astype(np.int32),
                        seg_off=seg_off, lab_row_off=lab_row_off, seg_lab_off=seg_lab_off,
                        label_study=label_study, sorted_pos=sorted_pos)
 
