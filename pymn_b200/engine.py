@@ -489,7 +489,15 @@ def network_from_ranked(rc: RankedCells, cell_label, seg_off, L, S, ndn=True, nb
     vmat = torch.empty((L, N), dtype=torch.float32, device=dev)
     _lib.call("mn_votes_finalize", votes, degree, cell_label, N, L, int(bool(ndn)), vmat, N)
     if t: t.start("auroc")
-    auc, n_pos = auroc(vmat, L, None, None, seg_off, S, cell_label, L)
+    if reduce_fn is not None and world > 1 and L >= world:
+        # every rank holds the reduced votes: the train columns (independent sorts) are dealt round-robin and
+        # the column slices of the table all-gathered, as in the centroid path
+        cols = torch.arange(rank, L, world, device=dev)
+        auc_loc, n_pos = auroc(vmat.index_select(0, cols).contiguous(), int(cols.numel()), None, None, seg_off, S,
+                               cell_label, L)
+        auc = _gather_columns(auc_loc, L, rank, world)
+    else:
+        auc, n_pos = auroc(vmat, L, None, None, seg_off, S, cell_label, L)
     if t: t.stop("auroc")
     return auc, n_pos, rc.flags, hist
 
