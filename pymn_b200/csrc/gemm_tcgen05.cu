@@ -61,7 +61,6 @@ struct GemmParams {
     int mt_step;      // ... of which every mt_step-th, starting at mt0 (row tiles dealt round-robin to GPUs)
     int n_tiles;      // number of column tiles
     int band;         // row tiles per L2 band of the tile schedule
-    int dbg_skip_col; // experiment switch (MN_DBG_SKIP_COL): drop the column-side reductions (wrong results)
     unsigned int* tile_counter;   // dynamic tile scheduler: next linear tile index (zeroed before the launch)
     int total_tiles;
     int stages;
@@ -426,7 +425,7 @@ struct LaneLabels {
 template <int BN>
 __device__ __forceinline__ void vote_merge_columns(const uint32_t* s_colw, const int32_t* s_wlab,
                                                    unsigned long long* votes, int64_t n0, int L, uint64_t pol_ef,
-                                                   int ew, int lane, bool skip) {
+                                                   int ew, int lane) {
     constexpr int HALF_COLS = BN / 2;
     const int et = ew * 32 + lane;
     const int lab0 = s_wlab[0];
@@ -438,7 +437,7 @@ __device__ __forceinline__ void vote_merge_columns(const uint32_t* s_colw, const
             const uint32_t* src = s_colw + (c / HALF_COLS) * 4 * HALF_COLS + (c % HALF_COLS);
             const unsigned long long sum = (unsigned long long)src[0] + src[HALF_COLS] +
                                            src[2 * HALF_COLS] + src[3 * HALF_COLS];
-            if (sum && !skip) red_add_u64_hint(votes + (n0 + c) * (int64_t)L + lab0, sum, pol_ef);
+            if (sum) red_add_u64_hint(votes + (n0 + c) * (int64_t)L + lab0, sum, pol_ef);
         }
     } else {
         const int my_lab = s_wlab[ew];
@@ -854,12 +853,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 // (a pair's 256-row tile is stored as two 128-row tiles: 2 * tile + rank)
                 const int sp_tile = tile * CTAS + (int)cta_rank;
                 const bool do_spill = p.spill != nullptr && sp_tile < p.spill_tiles;
-                const int sp_mode = p.dbg_skip_col >> 1;          // experiment switch MN_DBG_SPILL_MODE
-                const int sp_at = (sp_mode == 1) ? (sp_tile & 255) : sp_tile;
                 // the spill keeps the 8-warp layout [role][chunk]: role = (lane quarter, column half), BN/64 chunks
                 const int sp_role = ((q + 2) & 3) + 4 * (half / (EW / 8));
                 const int sp_chunk0 = (half % (EW / 8)) * (HALF_COLS / 32);
-                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)sp_at * (size_t)(BM * BN)) +
+                uint4* sp = reinterpret_cast<uint4*>(p.spill + (size_t)sp_tile * (size_t)(BM * BN)) +
                             (size_t)(sp_role * (BN / 64) + sp_chunk0) * 256 + lane;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
@@ -879,7 +876,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                     const int c = 4 * c4 + u;
                                     const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], half_bins, q_top);
                                     const bool use = ibv[u] > 0.f;
-                                    if (!p.dbg_skip_col) atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
+                                    atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
                                     r[c] = use ? qv : 0u;
                                 }
                             }
@@ -903,19 +900,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                         for (int c = 0; c < 32; ++c) r[c] = 0u;
                     }
                     if (do_spill) {
-                        if (sp_mode == 2) {
+                        // streaming stores (plain stores and an evict-first L2 hint measured the same)
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) sp[k * 32] = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-                        } else if (sp_mode == 3) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(sp + k * 32),
-                                             "r"(r[4 * k]), "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]), "l"(pol_ef) : "memory");
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                __stcs(sp + k * 32, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
-                        }
+                        for (int k = 0; k < 8; ++k)
+                            __stcs(sp + k * 32, make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]));
                         sp += 256;
                     }
                 }
@@ -974,7 +962,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 
             if (EPI == EPI_VOTE && p.tri != 0) {
                 epi_bar_sync<EPI_T>();
-                vote_merge_columns<BN>(s_colw, s_wlab, p.votes, n0, p.L, pol_ef, ew, lane, p.dbg_skip_col != 0);
+                vote_merge_columns<BN>(s_colw, s_wlab, p.votes, n0, p.L, pol_ef, ew, lane);
             }
         }
         if (EPI == EPI_HIST) {
@@ -1489,8 +1477,6 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     p.inv_b = inv_norm;
     p.nbins = nbins;
     p.hist = reinterpret_cast<unsigned long long*>(hist);
-    p.dbg_skip_col = getenv("MN_DBG_NOHIST") ? 1 : 0;      // experiment switch: no histogram atomics (wrong results)
-    if (const char* e = getenv("MN_DBG_SPILL_MODE")) p.dbg_skip_col |= atoi(e) << 1;   // 1: wrap into 32 MB (wrong), 2: plain st, 3: evict-first hint
     MN_CHECK_ARG(spill_tiles >= 0 && (spill_tiles == 0 || spill != nullptr), "mn_corr_hist: spill_tiles without a spill buffer");
     MN_CHECK_ARG((reinterpret_cast<uintptr_t>(spill) & 15) == 0, "mn_corr_hist: spill must be 16-byte aligned");
     p.spill_tiles = (int)(spill_tiles > INT_MAX ? INT_MAX : spill_tiles) & ~(ctas - 1);    // whole pairs only
@@ -1549,7 +1535,6 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     // symmetric network: compute the upper triangle only and add every weight to both cells
     // (MN_VOTE_FULL=1 computes all N^2 tiles instead; debugging aid)
     p.tri = getenv("MN_VOTE_FULL") ? 0 : 1;
-    p.dbg_skip_col = getenv("MN_DBG_SKIP_COL") ? 1 : 0;
     const bool wide = nbins <= 16384 && !getenv("MN_GEMM_BN128");
     const int ctas = p.tri ? corr_ctas(wide) : 1, bm = BM * ctas;
     MN_CHECK_ARG((row0 % bm) == 0, "mn_corr_vote: row0 must be a multiple of %d", bm);
