@@ -11,7 +11,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, prepare_matrix
+from .utils import label_layout, prepare_matrix, select_genes
 
 
 def _pvals(roc: np.ndarray, n_pos: np.ndarray, n_neg: np.ndarray) -> np.ndarray:
@@ -137,13 +137,13 @@ def MetaNeighborUS(adata,
                     ), "Study Col is a category type, cast to either string or int"
             assert (adata.obs[ct_col].dtype.name != "category"
                     ), "Cell Type Col is a category type, cast to either string or int"
-            cell_nv = metaNeighborUS_fast(adata[:, var_genes].X, adata.obs[study_col], adata.obs[ct_col],
+            cell_nv = metaNeighborUS_fast(select_genes(adata, var_genes).X, adata.obs[study_col], adata.obs[ct_col],
                                           node_degree_normalization, one_vs_best, compute_p)
         else:
-            cell_nv = metaNeighborUS_default(adata[:, var_genes], study_col, ct_col, node_degree_normalization,
+            cell_nv = metaNeighborUS_default(select_genes(adata, var_genes), study_col, ct_col, node_degree_normalization,
                                              compute_p)
     else:
-        cell_nv = MetaNeighborUS_from_trained(trained_model, adata[:, var_genes].X, adata.obs[study_col].values,
+        cell_nv = MetaNeighborUS_from_trained(trained_model, select_genes(adata, var_genes).X, adata.obs[study_col].values,
                                               adata.obs[ct_col].values, node_degree_normalization, one_vs_best,
                                               compute_p)
     if compute_p:

@@ -5,7 +5,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, prepare_matrix
+from .utils import label_layout, prepare_matrix, select_genes
 
 
 def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
@@ -25,7 +25,7 @@ def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
         var_genes = adata.var_names[np.asarray(adata.var[var_genes].values, dtype=bool)]
     assert var_genes.shape[0] > 2, "Must have at least 2 genes"
 
-    sub = adata[:, var_genes]
+    sub = select_genes(adata, var_genes)
     X = engine.start_upload(prepare_matrix(sub.X))       # the upload runs while the host encodes the labels
     S = np.asarray(sub.obs[study_col].values, dtype=object)
     C = np.asarray(sub.obs[ct_col].values, dtype=object)

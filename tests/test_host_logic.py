@@ -135,3 +135,19 @@ def test_model_csv_round_trip(tmp_path):
     bad.index = ["cells"] + genes
     with pytest.raises(AssertionError):
         pymn_b200.save_model(bad, tmp_path / "bad.csv")
+
+
+def test_select_genes_identity_is_free():
+    """Selecting every gene in order must not copy the matrix; any other selection slices as the reference does."""
+    from pymn_b200.utils import select_genes
+    rng = np.random.default_rng(1)
+    x = rng.poisson(1.0, size=(20, 6)).astype(np.float32)
+    inp = dict(X=x, study=np.array(["a"] * 20, dtype=object), ctype=np.array(["t"] * 20, dtype=object),
+               genes=np.array([f"g{i}" for i in range(6)], dtype=object), hvg=np.ones(6, bool))
+    ad = make_adata(inp)
+    assert select_genes(ad, ad.var_names) is ad
+    assert select_genes(ad, ad.var_names[np.ones(6, bool)]) is ad
+    sub = select_genes(ad, ad.var_names[[0, 2, 5]])
+    assert sub is not ad and np.array_equal(sub.X, x[:, [0, 2, 5]])
+    rev = select_genes(ad, ad.var_names[::-1])
+    assert rev is not ad and np.array_equal(rev.X, x[:, ::-1])
