@@ -151,3 +151,52 @@ def test_select_genes_identity_is_free():
     assert sub is not ad and np.array_equal(sub.X, x[:, [0, 2, 5]])
     rev = select_genes(ad, ad.var_names[::-1])
     assert rev is not ad and np.array_equal(rev.X, x[:, ::-1])
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("kind", ["object", "arrow", "int", "bar"])
+def test_label_layout_randomised_against_plain_python(seed, kind):
+    """label_layout (Arrow / hash factorisation, O(N) pair coding, radix argsort) against a direct restatement
+    of what the reference builds: joined 'study|type' strings, np.unique order, per-study sorted rows."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 400))
+    st_pool = ["s1", "s10", "s2", "S", "a b", "z|z" if kind == "bar" else "zz"][: int(rng.integers(1, 6))]
+    ct_pool = ["t1", "t10", "T", "x y", "é", "t2", "a"][: int(rng.integers(1, 7))]
+    if kind == "int":
+        study = rng.integers(0, 12, size=n)
+        ctype = rng.integers(-3, 20, size=n)
+    else:
+        study = np.array([st_pool[i] for i in rng.integers(0, len(st_pool), size=n)], dtype=object)
+        ctype = np.array([ct_pool[i] for i in rng.integers(0, len(ct_pool), size=n)], dtype=object)
+    s_in, c_in = study, ctype
+    if kind == "arrow":
+        df = pd.DataFrame({"s": study, "c": ctype})
+        s_in, c_in = df["s"].values, df["c"].values            # pandas string arrays (Arrow-backed on pandas 3)
+    replace_bar = kind == "bar"
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lay = label_layout(s_in, c_in, replace_bar=replace_bar)
+    s_str = [str(v).replace("|", ".") if replace_bar else str(v) for v in study.tolist()]
+    c_str = [str(v) for v in ctype.tolist()]
+    joined = [a + "|" + b for a, b in zip(s_str, c_str)]
+    if kind == "int":
+        st_sorted = [str(v) for v in np.unique(study).tolist()]           # numeric order, as np.unique on ints
+    else:
+        st_sorted = sorted(set(str(v) for v in study.tolist()))           # studies sorted BEFORE the bar replacement
+        st_sorted = [v.replace("|", ".") if replace_bar else v for v in st_sorted]
+    rows = []
+    for st in st_sorted:
+        rows += sorted({j for j, s in zip(joined, s_str) if s == st})
+    assert list(lay.row_labels) == rows
+    assert [lay.row_labels[c] for c in lay.cell_label] == [joined[i] for i in lay.perm]
+    assert sorted(lay.perm.tolist()) == list(range(n))
+    # stable within a label: input order preserved
+    for lab in range(len(rows)):
+        idx = lay.perm[lay.lab_row_off[lab]:lay.lab_row_off[lab + 1]]
+        assert np.all(np.diff(idx) > 0)
+    assert [lay.row_labels[i] for i in np.argsort(lay.sorted_pos)] == sorted(rows)
+    assert lay.seg_off[-1] == n and lay.lab_row_off[-1] == n
+    for t in range(len(st_sorted)):
+        assert set(lay.cell_study[lay.seg_off[t]:lay.seg_off[t + 1]].tolist()) <= {t}
