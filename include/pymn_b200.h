@@ -159,9 +159,15 @@ int mn_corr_hist(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
  * the GEMM forms).  spill_tiles is rounded down to whole cluster tiles (2 stored tiles per CTA pair). */
 int mn_corr_spill_layout(int64_t N, int64_t row0, int64_t row1, int32_t shard_rank, int32_t shard_world,
                          int32_t nbins, int64_t* n_tiles /* host */, int64_t* tile_bytes /* host */);
-/* n_diag = number of diagonal entries (all cells, they tie at rho = 1 -- utils.py:72) */
-/* lut uint32 [nbins + 2]: lut[b] = W_fix at the lower edge of bin b, lut[nbins] = at the upper edge of the
- * last bin, lut[nbins + 1] = 1 if some bin rises by more than 2047 (pass 2 then uses its two-load lookup) */
+/* hist -> packed CDF table.  n_diag = number of diagonal entries (all cells; they tie at rho = 1, utils.py:72).
+ * lut uint32 [nbins + 2]: lut[b] = (W0 << 11) | rise for bin b, W in 2^20 fixed point:
+ *   rise > 0: W0 = weight at the lower edge of the bin, rising linearly by `rise` (< 2047) across it;
+ *   rise = 0: the bin holds >= 0.2 % of all pairs -- one tie block of heavily tied correlations (gene sets of a
+ *             handful of genes) -- and W0 is the block's MID-rank weight, the rank bottleneck.rankdata gives
+ *             every member of a tie block (utils.py:45).
+ * lut[nbins] = weight at the top edge (rise 0); lut[nbins + 1] = number of tie-block bins (diagnostic).
+ * Bin of a correlation: floor(rho * (nbins/2 - 0.81) + nbins/2 + 0.043) -- the odd constants keep simple
+ * fractions (rho = 1/2, 1/4 ...) away from the bin edges, where FP32 rounding would split their tie block. */
 int mn_corr_lut(const uint64_t* hist, int32_t nbins, int64_t n_diag, uint32_t* lut /* [nbins+2] */,
                 mn_stream_t stream);
 int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,

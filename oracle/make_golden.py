@@ -100,8 +100,28 @@ def run_reference(name, spec):
     return inp, out
 
 
+def main_big(only):
+    """BASELINE-shaped cases: outputs + input digests only (oracle/cases.py BIG_CASES)."""
+    import time
+    for name, spec in C.BIG_CASES.items():
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        inp, out = run_reference(name, spec)
+        payload = {f"out_{k}": v for k, v in out.items() if not k.startswith("model_")}
+        payload["spec"] = np.asarray(json.dumps(spec, sort_keys=True))
+        payload["in_sha256"] = np.asarray(C.inputs_digest(inp))
+        if "train" in spec:
+            payload["train_sha256"] = np.asarray(C.inputs_digest(C.build_inputs(spec["train"])))
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **payload)
+        print(f"{name}: wrote {path} ({os.path.getsize(path)} bytes, reference took {time.time() - t0:.0f} s)", flush=True)
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--big" in sys.argv[1:]:
+        return main_big(set(a for a in sys.argv[1:] if a != "--big"))
     only = set(sys.argv[1:])
     for name, spec in C.CASES.items():
         if only and name not in only:

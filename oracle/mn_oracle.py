@@ -142,6 +142,9 @@ def compute_aurocs(votes: np.ndarray, codes: np.ndarray, n_labels: int):
     votes = np.asarray(votes, np.float64)
     n_t = votes.shape[0]
     ranks = rankdata_avg(votes, axis=0)
+    # a NaN vote makes the whole column's ranks NaN (scipy.stats.rankdata's nan_policy="propagate", which
+    # stands in for bottleneck.rankdata here -- oracle/ref_loader.py); only score_low_mem can produce one
+    ranks[:, np.isnan(votes).any(axis=0)] = np.nan
     n_pos = np.bincount(codes, minlength=n_labels).astype(np.float64)
     n_neg = n_t - n_pos
     sum_pos = _onehot(codes, n_labels).T @ ranks

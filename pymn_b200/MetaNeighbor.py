@@ -110,16 +110,17 @@ def MetaNeighbor(
     col_lists = [np.flatnonzero(gs_values[:, j]).astype(np.int32) for j in mine]
     offs = np.concatenate([[0], np.cumsum([len(c) for c in col_lists])]).astype(np.int64)
     all_cols = engine._i32(np.concatenate(col_lists) if col_lists else np.zeros(0, np.int32))
-    tables = []
-    for jj in range(len(mine)):
-        tables.append(engine.supervised_geneset(ctx, all_cols[offs[jj]:offs[jj + 1]], K,
-                                                bool(node_degree_normalization), bool(fast_version)))
+    # fast_version: a cell that is constant and non-zero over a gene set turns the reference's whole result
+    # for that set into NaN (MetaNeighbor.py:121-130); flagged on the device, applied here
     local = np.full((K, len(mine)), np.nan)
-    if tables:
-        import torch
-        stacked = torch.stack(tables).cpu().numpy()              # one device -> host copy
+    if len(mine):
+        tables, poison = engine.supervised_tables(ctx, all_cols, offs, K, bool(node_degree_normalization),
+                                                  bool(fast_version))
+        stacked = tables.cpu().numpy()                           # one device -> host copy
+        poisoned = poison.cpu().numpy()
         for jj in range(len(mine)):
-            local[:, jj] = _reduce_over_studies(stacked[jj], S, K)
+            if not poisoned[jj]:
+                local[:, jj] = _reduce_over_studies(stacked[jj], S, K)
     table = gather_columns(local, n_sets, rank, world)
     results = pd.DataFrame(table, index=ct_names, columns=genesets.columns)
     if save_uns:

@@ -274,37 +274,33 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// position of rho on the bin axis; pass 1 and pass 2 must agree bit for bit
-__device__ __forceinline__ float rho_binpos(float acc, float inv_i_half, float inv_j, float half_bins) {
-    return fmaf(acc * inv_i_half, inv_j, half_bins);      // (rho + 1) * nbins / 2
+// Position of rho on the bin axis; pass 1 and pass 2 must agree bit for bit.
+//   pos = rho * bin_scale + bin_offset,  bin_scale = nbins/2 - 0.81,  bin_offset = nbins/2 + 0.043
+// so rho in [-1, 1] maps into (0.85, nbins - 0.76).  The odd constants keep "nice" correlations off the
+// bin edges: with pos = (rho + 1) * nbins / 2 every rho = k / 2^m sat exactly ON an edge, and the FP32
+// rounding of inv_i * inv_j dealt the members of one tie block (tiny gene sets: thousands of cell pairs
+// share rho = 1/2) to the two bins around it -- half of the block then ranked a whole bin too low.
+__host__ __device__ __forceinline__ float bin_scale(int nbins) { return 0.5f * (float)nbins - 0.81f; }
+__host__ __device__ __forceinline__ float bin_offset(int nbins) { return 0.5f * (float)nbins + 0.043f; }
+__device__ __forceinline__ float rho_binpos(float acc, float inv_i_s, float inv_j, float offset) {
+    return fmaf(acc * inv_i_s, inv_j, offset);
 }
 // ... as 16.16 fixed point: bin = q >> 16, position inside the bin = q & 0xffff.  NaN (a dropped
 // cell's scale) and negative values convert to 0.  This integer is what pass 1 bins, what the rho
 // spill stores and what pass 2 maps to a weight, so the three can never disagree.
 constexpr int Q_FRAC_BITS = 16;
-__device__ __forceinline__ uint32_t rho_q(float acc, float inv_i_half, float inv_j, float half_bins, uint32_t q_top) {
-    return min(__float2uint_rd(rho_binpos(acc, inv_i_half, inv_j, half_bins) * (float)(1 << Q_FRAC_BITS)), q_top);
+__device__ __forceinline__ uint32_t rho_q(float acc, float inv_i_s, float inv_j, float offset, uint32_t q_top) {
+    return min(__float2uint_rd(rho_binpos(acc, inv_i_s, inv_j, offset) * (float)(1 << Q_FRAC_BITS)), q_top);
 }
-// Shared-memory copy of the LUT, one packed word per bin: (W at the lower edge) << 11 | (rise across the bin).
-// tab has nbins + 2 entries: q <= nbins << 16 may address entry nbins (rise 0), and the two-load form reads one further.
-__device__ __forceinline__ uint32_t lut_pack(const uint32_t* lut, int i, int nbins) {
-    const uint32_t lo = lut[i < nbins ? i : nbins];
-    const uint32_t hi = lut[i + 1 < nbins ? i + 1 : nbins];
-    const uint32_t d = hi - lo;
-    return (lo << MN_LUT_DELTA_BITS) | (d < MN_LUT_DELTA_MAX ? d : MN_LUT_DELTA_MAX);
-}
-// W by linear interpolation inside the bin.  One load when every bin's rise fits the 11-bit field
-// (lut[nbins + 1] == 0, the normal case); otherwise (a bin holding more than 0.2 % of all pairs: tiny
-// gene sets with heavily tied rho) `wide` selects the two-load form, which reads the next entry's edge.
-// Both forms give the same integer whenever the rise fits.
+// The LUT (corr_lut_kernel) holds one packed word per bin: (W0 << 11) | rise.
+//   rise > 0: W0 = weight at the bin's lower edge, the weight rises linearly by `rise` across the bin;
+//   rise = 0: the bin is ONE TIE BLOCK (it holds >= 0.2 % of all pairs -- only heavily tied correlations of
+//             tiny gene sets do that) and W0 is the block's mid-rank weight, as bottleneck.rankdata gives a
+//             tie block (utils.py:45).
+// One shared-memory load per pair either way.
 __device__ __forceinline__ uint32_t w_from_q(uint32_t q, const uint32_t* tab) {
     const uint32_t e = tab[q >> Q_FRAC_BITS];
     return (e >> MN_LUT_DELTA_BITS) + (((e & MN_LUT_DELTA_MAX) * (q & ((1u << Q_FRAC_BITS) - 1u))) >> Q_FRAC_BITS);
-}
-__device__ __forceinline__ uint32_t w_from_q_wide(uint32_t q, const uint32_t* tab) {
-    const unsigned b = q >> Q_FRAC_BITS;
-    const uint32_t lo = tab[b] >> MN_LUT_DELTA_BITS, hi = tab[b + 1] >> MN_LUT_DELTA_BITS;
-    return lo + __umulhi(hi - lo, q << (32 - Q_FRAC_BITS));
 }
 
 // ------------------------------------------------------------------ pass-2 vote accumulation
@@ -343,7 +339,7 @@ struct VoteRows {
     // (otherwise 0: the mixed-label columns have been flushed to global memory already).
     template <typename LabSrc>
     __device__ __forceinline__ uint32_t chunk(uint32_t (&r)[32], unsigned brk, const LabSrc labs,
-                                              const uint32_t* s_table, bool wide, bool sym,
+                                              const uint32_t* s_table, bool sym,
                                               unsigned long long* vcol, int L, uint64_t pol_ef, int lane) {
         uint32_t mycol = 0u;
         if (brk & 1u) {                                  // warp-uniform: a label run starts with this chunk
@@ -353,20 +349,11 @@ struct VoteRows {
         if ((brk >> 1) == 0u) {
             // fast path (almost every chunk): one label run -> branch-free
             uint32_t acc32 = 0u;                         // 32 weights <= 2^20 each fit 32 bits
-            if (!wide) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const uint32_t w = w_from_q(r[c], s_table);
-                    acc32 += w;
-                    r[c] = w;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const uint32_t w = w_from_q_wide(r[c], s_table);
-                    acc32 += w;
-                    r[c] = w;
-                }
+            for (int c = 0; c < 32; ++c) {
+                const uint32_t w = w_from_q(r[c], s_table);
+                acc32 += w;
+                r[c] = w;
             }
             run_acc += acc32;
         } else {
@@ -376,7 +363,7 @@ struct VoteRows {
                     flush();
                     cur_lab = labs.at(c);
                 }
-                const uint32_t w = wide ? w_from_q_wide(r[c], s_table) : w_from_q(r[c], s_table);
+                const uint32_t w = w_from_q(r[c], s_table);
                 run_acc += w;
                 r[c] = w;
             }
@@ -620,7 +607,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     if (EPI != EPI_STORE) {
         // hist starts at zero; lut is copied in
         for (int i = threadIdx.x; i < p.nbins + 2; i += ALL_T)
-            s_table[i] = (EPI == EPI_VOTE) ? lut_pack(p.lut, i, p.nbins) : 0u;
+            s_table[i] = (EPI == EPI_VOTE) ? p.lut[i] : 0u;
     }
     tc_fence_before();
     __syncthreads();
@@ -783,7 +770,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
         int cur_tile = 0;
         int a = 0, qs = 0;
         uint32_t aph = 0, qph = 0;
-        const float half_bins = 0.5f * (float)p.nbins;
+        const float bscale = bin_scale(p.nbins), boff = bin_offset(p.nbins);
         const uint64_t pol_ef = l2_evict_first_policy();
         for (;;) {
             wait_queue(&qfull_bar[qs], qph);
@@ -844,9 +831,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     }
                 }
             } else if (EPI == EPI_HIST) {
-                const float inv_i_half = inv_i * half_bins;
+                const float inv_i_half = inv_i * bscale;
                 const unsigned sink = (unsigned)p.nbins + 1u;
-                const uint32_t q_top = (uint32_t)p.nbins << Q_FRAC_BITS;
+                const uint32_t q_top = ((uint32_t)p.nbins << Q_FRAC_BITS) - 1u;
                 const bool row_live = inv_i > 0.f;
                 // rho spill: this warp's 32 x 32 chunks in tile-native order, [ew][chunk][k][lane] x 16 B
                 // (coalesced 512-byte stores); masked entries are stored as 0, which maps to W = lut[0] = 0
@@ -874,7 +861,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
                                     const int c = 4 * c4 + u;
-                                    const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], half_bins, q_top);
+                                    const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], boff, q_top);
                                     const bool use = ibv[u] > 0.f;
                                     atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
                                     r[c] = use ? qv : 0u;
@@ -888,7 +875,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) {
                                     const int c = 4 * c4 + u;
-                                    const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], half_bins, q_top);
+                                    const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, ibv[u], boff, q_top);
                                     const bool use = ibv[u] > 0.f && (n0 + c0 + c > m);
                                     atomicAdd(&s_table[use ? (qv >> Q_FRAC_BITS) : sink], 1u);
                                     r[c] = use ? qv : 0u;
@@ -914,10 +901,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 // NaN propagates through the bin position, the float->uint conversion turns it into
                 // q = 0 and lut[0] == 0, so their weights vanish without a predicate in the inner loop.
                 const float qnan = __int_as_float(0x7fc00000);
-                const float inv_i_half = (inv_i > 0.f) ? inv_i * half_bins : qnan;
+                const float inv_i_half = (inv_i > 0.f) ? inv_i * bscale : qnan;
                 const bool sym = p.tri != 0;
-                const uint32_t q_top = (uint32_t)p.nbins << Q_FRAC_BITS;
-                const bool wide = p.lut[p.nbins + 1] != 0u;
+                const uint32_t q_top = ((uint32_t)p.nbins << Q_FRAC_BITS) - 1u;
                 VoteRows vr;
                 vr.begin(p.label[row_ok ? m : p.M - 1], p.votes + (row_ok ? m : 0) * (int64_t)p.L, lane);
                 uint32_t* colw = s_colw + ew * HALF_COLS;
@@ -930,20 +916,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                         for (int c4 = 0; c4 < 8; ++c4) {
                             const float4 ib = invb4[c4];
-                            r[4 * c4] = rho_q(__uint_as_float(r[4 * c4]), inv_i_half, ib.x, half_bins, q_top);
-                            r[4 * c4 + 1] = rho_q(__uint_as_float(r[4 * c4 + 1]), inv_i_half, ib.y, half_bins, q_top);
-                            r[4 * c4 + 2] = rho_q(__uint_as_float(r[4 * c4 + 2]), inv_i_half, ib.z, half_bins, q_top);
-                            r[4 * c4 + 3] = rho_q(__uint_as_float(r[4 * c4 + 3]), inv_i_half, ib.w, half_bins, q_top);
+                            r[4 * c4] = rho_q(__uint_as_float(r[4 * c4]), inv_i_half, ib.x, boff, q_top);
+                            r[4 * c4 + 1] = rho_q(__uint_as_float(r[4 * c4 + 1]), inv_i_half, ib.y, boff, q_top);
+                            r[4 * c4 + 2] = rho_q(__uint_as_float(r[4 * c4 + 2]), inv_i_half, ib.z, boff, q_top);
+                            r[4 * c4 + 3] = rho_q(__uint_as_float(r[4 * c4 + 3]), inv_i_half, ib.w, boff, q_top);
                         }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], half_bins, q_top);
+                            const uint32_t qv = rho_q(__uint_as_float(r[c]), inv_i_half, s_invb[c0 + c], boff, q_top);
                             const bool use = sym ? (n0 + c0 + c > m) : (n0 + c0 + c != m);
                             r[c] = use ? qv : 0u;
                         }
                     }
-                    const uint32_t mycol = vr.chunk(r, s_flush[c0 >> 5], SmemLabels{s_lab + c0}, s_table, wide,
+                    const uint32_t mycol = vr.chunk(r, s_flush[c0 >> 5], SmemLabels{s_lab + c0}, s_table,
                                                     sym, p.votes + (n0 + c0) * (int64_t)p.L, p.L, pol_ef, lane);
                     if (sym) colw[c0 - cbeg + lane] = mycol;
                 }
@@ -1024,8 +1010,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) vote_spill_kernel(const GemmPar
     unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_raw + (size_t)n_warps * (4096 + 8)) +
                                 (size_t)warp * (NCK * 32) + lane;
     uint32_t* s_table = reinterpret_cast<uint32_t*>(s_raw + (size_t)n_warps * (4096 + 8 + NCK * 32 * 8));   // [nbins + 2]
-    for (int i = threadIdx.x; i < p.nbins + 2; i += blockDim.x) s_table[i] = lut_pack(p.lut, i, p.nbins);
-    const bool wide = p.lut[p.nbins + 1] != 0u;
+    for (int i = threadIdx.x; i < p.nbins + 2; i += blockDim.x) s_table[i] = p.lut[i];
     if (lane == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1121,7 +1106,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) vote_spill_kernel(const GemmPar
                 // label runs of this chunk's columns: a run starts where the label differs from the previous column's
                 const unsigned brk = __ballot_sync(0xffffffffu, (k == 0 && lane == 0) || lab_prev != lab_k);
                 const int lab_use = lab_k < 0 ? 0 : lab_k;
-                const uint32_t mycol = vr.chunk(r, brk, LaneLabels{lab_use}, s_table, wide, true,
+                const uint32_t mycol = vr.chunk(r, brk, LaneLabels{lab_use}, s_table, true,
                                                 p.votes + (n0 + 32 * k) * (int64_t)p.L, p.L, pol_ef, lane);
                 if (mycol) s_col[k * 32] += mycol;
             }
@@ -1135,17 +1120,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) vote_spill_kernel(const GemmPar
 // hist: counts of rho over pairs i<j.  Ranking covers both triangles plus the
 // n_diag diagonal entries, which tie at the top (utils.py:72).  For a value at
 // fraction t of bin b:  rank - 1 ~= 2*(cum[b] + t*cnt[b]);  W = (rank-1)/top with
-// top = F - (n_diag-1)/2 - 1, F = 2*total + n_diag (utils.py:47-49).  lut[b] = W at the
-// lower edge of bin b in 2^MN_W_SHIFT fixed point, lut[nbins] = W at the upper edge.
+// top = F - (n_diag-1)/2 - 1, F = 2*total + n_diag (utils.py:47-49), in 2^MN_W_SHIFT fixed point.
+// Output: one packed word per bin, (W0 << 11) | rise (see w_from_q).  A bin whose weight would rise by
+// 2047 units or more holds >= 0.2 % of all pairs: that is a tie block (a few genes, heavily tied ranks),
+// and bottleneck.rankdata (utils.py:45) gives every member of a tie block its MID-rank -- so the bin gets
+// W0 = W(2 cum + cnt - 1/2) and rise 0 instead of an interpolation by the position inside the bin, which
+// would shift the whole block by up to half its size.  lut[nbins] = top edge (rise 0),
+// lut[nbins + 1] = number of such bins.
 __global__ void corr_lut_kernel(const unsigned long long* __restrict__ hist, int nbins, long long n_diag,
                                 uint32_t* __restrict__ lut) {
     __shared__ unsigned long long s_part[1024];
+    __shared__ int s_heavy;
     const int T = blockDim.x, tid = threadIdx.x;
     const int per = (nbins + T - 1) / T;
     const int b0 = tid * per, b1 = min(nbins, b0 + per);
     unsigned long long local = 0;
     for (int b = b0; b < b1; ++b) local += hist[b];
     s_part[tid] = local;
+    if (tid == 0) s_heavy = 0;
     __syncthreads();
     if (tid == 0) {
         unsigned long long run = 0;
@@ -1164,21 +1156,26 @@ __global__ void corr_lut_kernel(const unsigned long long* __restrict__ hist, int
     const double one = (double)MN_W_ONE;
     const double scale = one / top;
     unsigned long long run = s_part[tid];
+    int heavy = 0;
     for (int b = b0; b < b1; ++b) {
-        lut[b] = (uint32_t)fmin(one, rint(2.0 * (double)run * scale));
-        run += hist[b];
+        const unsigned long long cnt = hist[b];
+        uint32_t w0 = (uint32_t)fmin(one, rint(2.0 * (double)run * scale));
+        const uint32_t w1 = (uint32_t)fmin(one, rint(2.0 * (double)(run + cnt) * scale));
+        uint32_t rise = w1 - w0;
+        if (rise >= MN_LUT_DELTA_MAX) {
+            w0 = (uint32_t)fmin(one, rint((2.0 * (double)run + (double)cnt - 0.5) * scale));
+            rise = 0u;
+            ++heavy;
+        }
+        lut[b] = (w0 << MN_LUT_DELTA_BITS) | rise;
+        run += cnt;
     }
-    if (tid == 0) lut[nbins] = (uint32_t)fmin(one, rint(2.0 * total * scale));
-    // lut[nbins + 1]: does some bin rise by more than the packed LUT's 11-bit field holds?
+    if (heavy) atomicAdd(&s_heavy, heavy);
     __syncthreads();
-    __shared__ int s_wide;
-    if (tid == 0) s_wide = 0;
-    __syncthreads();
-    int widef = 0;
-    for (int b = b0; b < b1; ++b) widef |= (lut[b + 1] - lut[b] > MN_LUT_DELTA_MAX) ? 1 : 0;
-    if (widef) atomicOr(&s_wide, 1);
-    __syncthreads();
-    if (tid == 0) lut[nbins + 1] = (uint32_t)s_wide;
+    if (tid == 0) {
+        lut[nbins] = (uint32_t)fmin(one, rint(2.0 * total * scale)) << MN_LUT_DELTA_BITS;
+        lut[nbins + 1] = (uint32_t)s_heavy;
+    }
 }
 
 __global__ void vote_rowsum_kernel(const unsigned long long* __restrict__ votes, int64_t N, int L,

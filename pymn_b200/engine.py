@@ -249,7 +249,7 @@ def one_vs_best(votes, ncols, denom, col_denom, seg_lab_off, n_seg, lab_row_off,
 # pipelines
 # ---------------------------------------------------------------------------
 def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_train, train_study, n_train_studies,
-                             ndn: bool, ovb: bool):
+                             ndn: bool, ovb: bool, timer=None):
     """predict_and_score (MetaNeighborUS.py:310-387) for all test studies at once.
     C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids.
 
@@ -272,18 +272,25 @@ def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_tr
         C = C.index_select(0, rows).contiguous()
         n_valid = n_valid.index_select(0, rows).contiguous()
         train_study = train_study.index_select(0, cols).contiguous()
+    t = timer
     if n_loc > 0:
         n_b = n_loc + (n_train_studies if ndn else 0)
+        if t: t.start("votes_gemm")
         b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
         addend = n_valid[:n_b].contiguous() if ndn else None
         out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
+        if t: t.stop("votes_gemm")
         denom = out[n_loc:] if ndn else None
         col_denom = train_study if ndn else None
+        if t: t.start("auroc")
         auc, n_pos = auroc(out, n_loc, denom, col_denom, seg_off, n_seg, cell_label, n_lab)
+        if t: t.stop("auroc")
         res = auc
         if ovb:
+            if t: t.start("one_vs_best")
             res = one_vs_best(out, n_loc, denom, col_denom, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
                               cell_label, n_lab, auc)
+            if t: t.stop("one_vs_best")
     else:
         auc = res = torch.empty((n_lab, 0), dtype=torch.float64, device=dev)
         n_pos = torch.zeros((n_lab,), dtype=torch.int32, device=dev)
@@ -324,37 +331,63 @@ def ranked_cells(X, lay: LabelLayout, drop_mode=0) -> RankedCells:
     return rank_normalize(Xd, row_index=_i32(lay.perm), drop_mode=drop_mode)
 
 
-def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
-    """metaNeighborUS_fast.  X: numpy / torch float32 [N, G] (input cell order), CSR, or an upload in flight
-    (start_upload).  Returns dict(table [L, L] rows = test labels, cols = train labels (both row order),
-    auroc (one-vs-rest table), n_pos [L], flags uint8 [N] in device row order)."""
+def _host_tables(res, auc, n_pos, flags):
+    return dict(table=res.cpu().numpy(), auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(), flags=flags.cpu().numpy())
+
+
+def us_fast_device(X, lay: LabelLayout, ndn=True, ovb=False, timer=None):
+    """metaNeighborUS_fast with every result left on the device: (table, auroc, n_pos, flags)."""
+    t = timer
+    if t: t.start("rank_normalize")
     rc = ranked_cells(X, lay, 0)
+    if t: t.stop("rank_normalize")
     L, S = len(lay.row_labels), len(lay.studies)
+    if t: t.start("centroids")
     C, n_valid = centroids(rc, _i32(lay.lab_row_off), L, extra_rows=S)
     train_study = _i32(lay.label_study)
     if ndn:
         group_sum_into(C, n_valid, L, train_study, S, rc.G)
-    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, L, train_study, S, ndn, ovb)
-    return dict(table=res.cpu().numpy(), auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(),
-                flags=rc.flags.cpu().numpy())
+    if t: t.stop("centroids")
+    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, L, train_study, S, ndn, ovb, timer)
+    return res, auc, n_pos, rc.flags
+
+
+def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
+    """metaNeighborUS_fast.  X: numpy / torch float32 [N, G] (input cell order), CSR, or an upload in flight
+    (start_upload).  Returns dict(table [L, L] rows = test labels, cols = train labels (both row order),
+    auroc (one-vs-rest table), n_pos [L], flags uint8 [N] in device row order)."""
+    return _host_tables(*us_fast_device(X, lay, ndn, ovb))
+
+
+def us_pretrained_device(X, lay: LabelLayout, model_centroids, model_n, model_study,
+                         n_model_studies: int, ndn=True, ovb=False, timer=None):
+    """MetaNeighborUS_from_trained with every result left on the device.  The model arrays may be host
+    arrays or device tensors: centroids float [L_train, G] (rows = model columns), n [L_train], study int [L_train]."""
+    t = timer
+    if t: t.start("rank_normalize")
+    rc = ranked_cells(X, lay, 0)
+    if t: t.stop("rank_normalize")
+    if t: t.start("centroids")
+    Lt = int(model_centroids.shape[0])
+    dev = rc.d_hi.device
+    C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=dev)
+    C[:Lt, :rc.G] = (model_centroids if isinstance(model_centroids, torch.Tensor)
+                     else to_device(np.asarray(model_centroids, np.float32)))
+    n_valid = torch.zeros((Lt + n_model_studies,), dtype=torch.float32, device=dev)
+    n_valid[:Lt] = model_n if isinstance(model_n, torch.Tensor) else to_device(np.asarray(model_n, np.float32))
+    train_study = model_study if isinstance(model_study, torch.Tensor) else _i32(model_study)
+    if ndn:
+        group_sum_into(C, n_valid, Lt, train_study, n_model_studies, rc.G)
+    if t: t.stop("centroids")
+    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, Lt, train_study, n_model_studies, ndn, ovb, timer)
+    return res, auc, n_pos, rc.flags
 
 
 def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.ndarray, model_study: np.ndarray,
                   n_model_studies: int, ndn=True, ovb=False):
     """MetaNeighborUS_from_trained.  model_centroids float [L_train, G] (rows = model
     columns), model_n [L_train], model_study int [L_train]."""
-    rc = ranked_cells(X, lay, 0)
-    Lt = int(model_centroids.shape[0])
-    C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)
-    C[:Lt, :rc.G] = to_device(np.asarray(model_centroids, np.float32))
-    n_valid = torch.zeros((Lt + n_model_studies,), dtype=torch.float32, device=rc.d_hi.device)
-    n_valid[:Lt] = to_device(np.asarray(model_n, np.float32))
-    train_study = _i32(model_study)
-    if ndn:
-        group_sum_into(C, n_valid, Lt, train_study, n_model_studies, rc.G)
-    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, Lt, train_study, n_model_studies, ndn, ovb)
-    return dict(table=res.cpu().numpy(), auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(),
-                flags=rc.flags.cpu().numpy())
+    return _host_tables(*us_pretrained_device(X, lay, model_centroids, model_n, model_study, n_model_studies, ndn, ovb))
 
 
 def train_model(X, lay: LabelLayout):
@@ -759,11 +792,17 @@ def supervised_prepare(X, lay: LabelLayout) -> SupervisedContext:
 
 
 def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types: int, ndn=True, fast=False,
-                       nbins=DEFAULT_NBINS):
+                       nbins=DEFAULT_NBINS, poison_out: torch.Tensor = None):
     """One gene set.  ``col_index``: int32 device tensor of the set's gene columns.  The layout behind ``ctx``
     is that of JOINT labels study*K + type (all S*K ids, empty ranges allowed).  Returns the float64
     [S*K, K] AUROC table (rows = joint test labels) ON THE DEVICE: nothing here synchronises, so the
-    caller can keep enqueuing gene sets and fetch all tables with one copy."""
+    caller can keep enqueuing gene sets and fetch all tables with one copy.
+
+    ``poison_out`` (0-dim bool tensor, fast path): set when some cell is constant and NON-ZERO over the gene
+    set.  score_low_mem only drops cells whose sum is <= 0 (MetaNeighbor.py:121), so such a cell normalises
+    to a NaN row (utils.py:146-147) that poisons `voters @ voter_id` and the candidates' ranks: the
+    reference's result for the gene set is NaN for every cell type.  K1 drops the cell
+    (flag bit 0 without bit 1); the caller reproduces the NaN column from this flag."""
     S = ctx.n_studies
     K = n_types
     Xd = ctx.Xd
@@ -778,9 +817,28 @@ def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types:
         _lib.call("mn_loso_finalize", out, rc.M, 0, None, n_valid, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
         kept = rc.inv_norm > 0
         test_label = torch.where(kept, cell_label, torch.full_like(cell_label, -1))
+        if poison_out is not None:
+            poison_out.copy_(((rc.flags & 3) == 1).any())
     else:
         votes, degree, _, _ = corr_network_votes(rc, cell_label, S * K, nbins)
         _lib.call("mn_loso_finalize", votes, S * K, 1, degree, None, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
         test_label = cell_label
     auc, _ = auroc(vmat, K, None, None, ctx.seg_off, S, test_label, S * K)
     return auc
+
+
+def supervised_tables(ctx: SupervisedContext, all_cols: torch.Tensor, offs, n_types: int, ndn=True, fast=False,
+                      nbins=DEFAULT_NBINS):
+    """All gene sets of one rank, back to back on the current stream (MetaNeighbor.py:84-93).  ``all_cols``:
+    int32 device tensor, the gene columns of set j are all_cols[offs[j]:offs[j + 1]].  Returns
+    (tables float64 [n_sets, S*K, K] on the device, poison bool [n_sets] -- see supervised_geneset);
+    nothing synchronises."""
+    n_sets = len(offs) - 1
+    dev = ctx.Xd.device
+    S, K = ctx.n_studies, n_types
+    tables = torch.empty((n_sets, S * K, K), dtype=torch.float64, device=dev)
+    poison = torch.zeros((max(1, n_sets),), dtype=torch.bool, device=dev)
+    for j in range(n_sets):
+        tables[j] = supervised_geneset(ctx, all_cols[int(offs[j]):int(offs[j + 1])], K, ndn, fast, nbins,
+                                       poison_out=poison[j] if fast else None)
+    return tables, poison

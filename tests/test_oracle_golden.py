@@ -33,7 +33,8 @@ def test_unsupervised_tables(name):
     spec, inp, ref = C.load_case(name)
     got = oracle_run(spec, inp)
     assert_table_close(got["auroc_values"], got["auroc_rows"], got["auroc_cols"],
-                       ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"], TIGHT, name)
+                       ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"], TIGHT, name,
+                       skip_cols=spec.get("noise_cols"))
     if spec.get("p"):
         assert_table_close(got["pval_values"], got["pval_rows"], got["pval_cols"],
                            ref["pval_values"], ref["pval_rows"], ref["pval_cols"], 1e-9, name + " pval")
@@ -93,3 +94,19 @@ def test_variable_genes(name):
     assert [str(g) for g in got["genes"]] == [str(g) for g in ref["genes"]]
     assert np.array_equal(got["selected"], ref["selected"]), name
     assert 0 < ref["selected"].sum() < ref["selected"].size
+
+
+@pytest.mark.parametrize("name", ["big_default_c2_4k", "big_fast_c4", "big_pretrained_c5"])
+def test_big_cases_rebuild_and_match(name):
+    """BASELINE-shaped fixtures (outputs + input digest only): the seeded inputs rebuild to the digest the
+    reference saw, and the oracle reproduces the reference's table.  At these sizes near-tied votes exist, so
+    the float64 restatement is allowed one rank flip per cell (summation order differs from the reference's
+    BLAS calls); the 16k-cell and one-vs-best fixtures take minutes of CPU and are left to the GPU tests."""
+    spec, inp, ref = C.load_big_case(name)
+    train_inp = C.build_inputs(spec["train"]) if "train" in spec else None
+    got = oracle_run(spec, inp, train_inp)
+    s = np.asarray(inp["study"], dtype=object)
+    n_t = min(int((s == st).sum()) for st in set(s.tolist()))
+    n_p = min(np.unique(O.join_labels(s, inp["ctype"]).astype(str), return_counts=True)[1])
+    assert_table_close(got["auroc_values"], got["auroc_rows"], got["auroc_cols"],
+                       ref["auroc_values"], ref["auroc_rows"], ref["auroc_cols"], 1.01 / (n_p * (n_t - n_p)), name)
