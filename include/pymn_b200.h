@@ -207,10 +207,10 @@ int mn_loso_finalize(const void* in, int64_t ldi, int32_t is_fixed, const uint64
  *   auroc     float64 [n_labels, ncols]: rows = test labels, cols = train labels
  *               (a label's row is filled from the segment its cells are in)
  *   n_pos     int32 [n_labels] or NULL: kept cells per test label
- *   workspace from mn_auroc_workspace_bytes(ncols, M)
+ *   workspace from mn_auroc_workspace_bytes(ncols, M, n_seg, n_labels)
  * Ranks are exact average-tie ranks of the float32 keys (integer 2*rank sums).
  */
-int64_t mn_auroc_workspace_bytes(int32_t ncols, int64_t M);
+int64_t mn_auroc_workspace_bytes(int32_t ncols, int64_t M, int32_t n_seg, int32_t n_labels);
 int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom, const int32_t* col_denom,
              const int32_t* seg_off, int32_t n_seg, const int32_t* cell_label, int32_t n_labels, int64_t M,
              double* auroc, int32_t* n_pos, void* workspace, int64_t workspace_bytes, mn_stream_t stream);

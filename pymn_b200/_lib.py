@@ -36,7 +36,7 @@ SIGNATURES = {
     "mn_corr_vote": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "mn_votes_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "mn_loso_finalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
-    "mn_auroc_workspace_bytes": (_i64, [_i32, _i64]),
+    "mn_auroc_workspace_bytes": (_i64, [_i32, _i64, _i32, _i32]),
     "mn_auroc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp]),
     "mn_one_vs_best": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "mn_debug_votes_simt": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
@@ -103,5 +103,5 @@ def corr_spill_layout(n: int, row0: int, row1: int, shard_rank: int, shard_world
     return int(nt.value), int(tb.value)
 
 
-def auroc_workspace_bytes(ncols: int, m: int) -> int:
-    return int(load().mn_auroc_workspace_bytes(ncols, m))
+def auroc_workspace_bytes(ncols: int, m: int, n_seg: int, n_labels: int) -> int:
+    return int(load().mn_auroc_workspace_bytes(ncols, m, n_seg, n_labels))

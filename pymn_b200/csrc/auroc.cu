@@ -1,4 +1,5 @@
-// K6: rank-sum AUROC, K7: one-vs-best.
+// K6 (sort form, used beyond 2,048 test labels; the product kernel is auroc_count.cu): rank-sum AUROC,
+// K7: one-vs-best.
 //
 // K6 replaces compute_aurocs (reference pymn/utils.py:151-178: rankdata over
 // the test cells of one study per train column, positives.T @ ranks),
@@ -520,9 +521,22 @@ one_vs_best_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, cons
 
 extern "C" {
 
-int64_t mn_auroc_workspace_bytes(int32_t ncols, int64_t M) {
+static int64_t sort_workspace_bytes(int32_t ncols, int64_t M) {
     const int64_t per = ((M + 63) / 64) * 64;
     return (int64_t)ncols * per * (4 + 4 + 2 + 2) + 1024;
+}
+
+// The counting kernel (auroc_count.cu) packs (key remainder | segment-local label) into 32 bits: up to 2,048
+// labels.  Beyond that (or with MN_AUROC_SORT=1, for A/B measurements) the radix-sort kernel above is used.
+static bool use_sort_kernel(int32_t n_labels) {
+    if (n_labels > 2048) return true;
+    const char* e = getenv("MN_AUROC_SORT");
+    return e && atoi(e) != 0;
+}
+
+int64_t mn_auroc_workspace_bytes(int32_t ncols, int64_t M, int32_t n_seg, int32_t n_labels) {
+    if (use_sort_kernel(n_labels)) return sort_workspace_bytes(ncols, M);
+    return mn::auroc_count_workspace_bytes(ncols, M, n_seg, n_labels);
 }
 
 int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom, const int32_t* col_denom,
@@ -531,45 +545,37 @@ int mn_auroc(const float* votes, int64_t ldv, int32_t ncols, const float* denom,
     MN_CHECK_ARG(votes && seg_off && cell_label && auroc && workspace, "mn_auroc: null pointer");
     MN_CHECK_ARG(ncols >= 1 && n_seg >= 1 && n_labels >= 1 && M >= 1 && ldv >= M, "mn_auroc: bad shape");
     MN_CHECK_ARG(n_labels <= 16000, "mn_auroc: n_labels=%d > 16000 unsupported", n_labels);
-    MN_CHECK_ARG(M < (1ll << 31), "mn_auroc: M too large");
-    MN_CHECK_ARG(workspace_bytes >= mn_auroc_workspace_bytes(ncols, M), "mn_auroc: workspace too small");
+    MN_CHECK_ARG(M < (1ll << 30), "mn_auroc: M too large");
+    MN_CHECK_ARG(workspace_bytes >= mn_auroc_workspace_bytes(ncols, M, n_seg, n_labels), "mn_auroc: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!use_sort_kernel(n_labels))
+        return mn::launch_auroc_count(votes, ldv, ncols, denom, col_denom, seg_off, n_seg, cell_label, n_labels, M, auroc,
+                                      n_pos, workspace, st);
     const int64_t per = ((M + 63) / 64) * 64;
     unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
     uint32_t* keys0 = reinterpret_cast<uint32_t*>(w);
     uint32_t* keys1 = keys0 + (int64_t)ncols * per;
     uint16_t* labs0 = reinterpret_cast<uint16_t*>(keys1 + (int64_t)ncols * per);
     uint16_t* labs1 = labs0 + (int64_t)ncols * per;
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t tot = (int64_t)n_labels * ncols;
     mn::fill_f64_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(auroc, tot, nan(""));
     MN_LAUNCH_CHECK();
     if (n_pos) MN_CUDA(cudaMemsetAsync(n_pos, 0, sizeof(int32_t) * n_labels, st));
-    // experimental sample-sort kernel (auroc_ss.cu): same results, not faster yet (both ~11 G votes/s) -- opt-in
-    if (getenv("MN_AUROC_SS"))
-        return mn::launch_auroc_ss(votes, ldv, ncols, denom, col_denom, seg_off, n_seg, cell_label, n_labels, per, auroc,
-                                   n_pos, keys0, keys1, labs0, labs1, st);
     const size_t dyn = (size_t)n_labels * 12 + 16;
     dim3 grid((unsigned)ncols, (unsigned)n_seg);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // many segments -> 256-thread CTAs (more of them per SM); few -> 512 threads per segment
-    bool small_cta = (int64_t)ncols * n_seg >= 8ll * sms;
-    if (const char* e = getenv("MN_AUROC_AT")) small_cta = atoi(e) == 256;      // tuning knob
-    // (the kernels' static shared memory is ~28-47 KB: any dynamic part needs the opt-in)
-    static size_t configured[2] = {0, 0};
+    const bool small_cta = (int64_t)ncols * n_seg >= 8ll * sms;
+    // (the kernels' static shared memory is ~28-47 KB: any dynamic part needs the opt-in; set on every call --
+    // the attribute is per device and a process may drive several)
     if (small_cta) {
-        if (dyn > configured[0]) {
-            MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            configured[0] = dyn;
-        }
+        MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         mn::auroc_kernel<256, 8><<<grid, 256, dyn, st>>>(votes, ldv, ncols, denom, col_denom, seg_off, cell_label, n_labels,
                                                         per, auroc, n_pos, keys0, keys1, labs0, labs1);
     } else {
-        if (dyn > configured[1]) {
-            MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            configured[1] = dyn;
-        }
+        MN_CUDA(cudaFuncSetAttribute(mn::auroc_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         mn::auroc_kernel<512, 8><<<grid, 512, dyn, st>>>(votes, ldv, ncols, denom, col_denom, seg_off, cell_label, n_labels,
                                                         per, auroc, n_pos, keys0, keys1, labs0, labs1);
     }

@@ -37,11 +37,11 @@ void count_launch(int n = 1);
 int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                      __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
                      int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr);
-// auroc_ss.cu
-int launch_auroc_ss(const float* votes, int64_t ldv, int ncols, const float* denom, const int32_t* col_denom,
-                    const int32_t* seg_off, int n_seg, const int32_t* cell_label, int n_labels, int64_t per,
-                    double* auroc, int32_t* n_pos, uint32_t* keys0, uint32_t* keys1, uint16_t* labs0, uint16_t* labs1,
-                    cudaStream_t st);
+// auroc_count.cu
+int64_t auroc_count_workspace_bytes(int ncols, int64_t M, int n_seg, int n_labels);
+int launch_auroc_count(const float* votes, int64_t ldv, int ncols, const float* denom, const int32_t* col_denom,
+                       const int32_t* seg_off, int n_seg, const int32_t* cell_label, int n_labels, int64_t M,
+                       double* auroc, int32_t* n_pos, void* workspace, cudaStream_t st);
 // rank_count.cu
 int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                       __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,

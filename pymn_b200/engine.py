@@ -230,7 +230,7 @@ def auroc(votes: torch.Tensor, ncols: int, denom, col_denom, seg_off: torch.Tens
     dev = votes.device
     out = torch.empty((n_labels, ncols), dtype=torch.float64, device=dev)
     n_pos = torch.empty((n_labels,), dtype=torch.int32, device=dev)
-    wbytes = _lib.auroc_workspace_bytes(ncols, M)
+    wbytes = _lib.auroc_workspace_bytes(ncols, M, n_seg, n_labels)
     ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
     _lib.call("mn_auroc", votes, int(votes.stride(0)), ncols, denom, col_denom, seg_off, n_seg, cell_label,
               n_labels, M, out, n_pos, ws, wbytes)

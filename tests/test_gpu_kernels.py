@@ -189,6 +189,98 @@ def test_auroc_kernel_matches_oracle(eng, n_seg, seg_n, ncols, n_labels, ties):
     assert np.array_equal(n_pos.cpu().numpy(), cnt)
 
 
+def _exact_auroc(key_f32, lab, n_labels):
+    """Rank-sum AUROC of every label from the exact average-tie ranks (integers x 2), utils.py:172-178."""
+    keep = lab >= 0
+    k, l = key_f32[keep], lab[keep]
+    r = __import__("scipy.stats", fromlist=["rankdata"]).rankdata(k.astype(np.float64), method="average")
+    out = np.full(n_labels, np.nan)
+    n = k.shape[0]
+    for c in np.unique(l):
+        pos = l == c
+        n_p = float(pos.sum())
+        roc = (r[pos].sum() / n_p - (n_p + 1.0) / 2.0) / float(n - n_p) if n - n_p > 0 else np.nan
+        out[c] = roc
+    return out
+
+
+@pytest.mark.parametrize("shape", ["skewed_71k", "giant_tie_60k", "many_tie_blocks", "wide_range", "two_values",
+                                   "dense_cluster_100k", "unsorted_labels", "million"])
+def test_auroc_counting_kernel_adversarial(eng, shape):
+    """The counting kernel (auroc_count.cu) at the sizes and distributions that stress its binning: several rounds
+    per segment, a long-tailed vote distribution, a tie block larger than one round, thousands of tie blocks,
+    keys spread over many binades and both signs, one coarse bin holding more than a round of distinct keys
+    (recursive refinement), labels in arbitrary cell order, a 1M-cell segment.  Bit-identical to exact ranks."""
+    rng = np.random.default_rng(__import__("zlib").crc32(shape.encode()))
+    ncols, n_labels = 3, 37
+    if shape == "skewed_71k":
+        n = 71429
+        votes = (0.0063 + rng.gamma(1.2, 0.0002, size=(ncols, n))).astype(np.float32)
+        votes[:, ::150] += 0.003
+    elif shape == "giant_tie_60k":
+        n = 90000
+        votes = rng.normal(size=(ncols, n)).astype(np.float32)
+        votes[:, rng.permutation(n)[:60000]] = 0.125
+    elif shape == "many_tie_blocks":
+        n = 50000
+        votes = np.round(rng.normal(size=(ncols, n)), 2).astype(np.float32)
+        votes[1] = np.round(votes[1], 0)
+    elif shape == "wide_range":
+        n = 66000
+        votes = (rng.normal(size=(ncols, n)) * np.exp(rng.uniform(-30, 30, size=(ncols, n)))).astype(np.float32)
+        votes[2, :100] = 0.0
+        votes[2, 100:200] = -0.0
+    elif shape == "two_values":
+        n = 120000
+        votes = rng.integers(0, 2, size=(ncols, n)).astype(np.float32)
+    elif shape == "dense_cluster_100k":
+        n = 150000                        # 100k distinct keys inside a sliver of the range: one coarse bin > one round
+        votes = rng.uniform(0.0, 1000.0, size=(ncols, n)).astype(np.float32)
+        votes[:, :100000] = (500.0 + rng.uniform(0.0, 0.01, size=(ncols, 100000))).astype(np.float32)
+    elif shape == "unsorted_labels":
+        n = 30000
+        votes = rng.normal(size=(ncols, n)).astype(np.float32)
+    else:
+        n = 1000000
+        votes = rng.normal(size=(ncols, n)).astype(np.float32)
+    lab = np.sort(rng.integers(0, n_labels, size=n)).astype(np.int32)
+    if shape == "unsorted_labels":
+        lab = rng.integers(0, n_labels, size=n).astype(np.int32)
+    lab[rng.random(n) < 0.03] = -1
+    seg_off = np.array([0, n], np.int32)
+    auc, n_pos = eng.auroc(eng.to_device(votes), ncols, None, None, eng._i32(seg_off), 1, eng._i32(lab), n_labels)
+    torch.cuda.synchronize()
+    got = auc.cpu().numpy()
+    for c in range(ncols):
+        ref = _exact_auroc(votes[c], lab, n_labels)
+        assert np.array_equal(np.isnan(got[:, c]), np.isnan(ref)), (shape, c)
+        assert np.nanmax(np.abs(got[:, c] - ref), initial=0) == 0.0, (shape, c)
+    assert np.array_equal(n_pos.cpu().numpy(), np.bincount(lab[lab >= 0], minlength=n_labels))
+
+
+def test_auroc_counting_equals_sort_kernel(eng, monkeypatch):
+    """Counting kernel == radix-sort kernel (the form kept for > 2,048 labels), many segments of uneven length,
+    node-degree denominators, 300 labels."""
+    rng = np.random.default_rng(11)
+    lens = rng.integers(1, 30000, size=6)
+    lens[2] = 0
+    M, ncols, n_labels = int(lens.sum()), 7, 300
+    seg_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    votes = (rng.normal(size=(ncols + 2, M)) * 0.01 + 1.0).astype(np.float32)
+    lab = np.concatenate([np.sort(rng.integers(0, 50, size=k)) + 50 * s for s, k in enumerate(lens)]).astype(np.int32)
+    lab[rng.random(M) < 0.02] = -1
+    col_denom = eng._i32((np.arange(ncols) % 2).astype(np.int32))
+    vd = eng.to_device(votes)
+    a1, p1 = eng.auroc(vd, ncols, vd[ncols:], col_denom, eng._i32(seg_off), len(lens), eng._i32(lab), n_labels)
+    monkeypatch.setenv("MN_AUROC_SORT", "1")
+    a2, p2 = eng.auroc(vd, ncols, vd[ncols:], col_denom, eng._i32(seg_off), len(lens), eng._i32(lab), n_labels)
+    monkeypatch.delenv("MN_AUROC_SORT")
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2)
+    assert torch.equal(torch.isnan(a1), torch.isnan(a2))
+    assert torch.equal(torch.nan_to_num(a1), torch.nan_to_num(a2))
+
+
 def test_one_vs_best_kernel_matches_oracle(eng):
     rng = np.random.default_rng(3)
     n_seg, per_seg, ncols = 2, 7, 11
