@@ -351,9 +351,15 @@ def test_corr_hist_and_votes(eng, n, g):
     gd = degree.cpu().numpy()
     gv = votes.cpu().numpy()
     assert np.array_equal(gv.sum(axis=1), gd), "votes over all labels add up to the node degree (exact integers)"
+    # g <= 256: every partial sum of the tensor core is an exact integer and so are the sums below.  Beyond, the
+    # FP32 accumulator truncates (one chain of ceil(g / 16) adds per plane product: ~6e-6 relative at g = 2,000,
+    # four plane products in that one chain at g = 2,100: ~5e-5), which moves rho by that much against the exact integer dot products of
+    # the host restatement -- the effect on the AUROC table is what tests/test_gpu_headline.py bounds
+    tol_w = 1e-5 if g <= 2048 else 1e-4
     rel = np.abs(gd - ref_deg).max() / ref_deg.max()
-    assert rel < 1e-5, f"node degree off by {rel:.2e}"
-    assert np.abs(gv - ref_votes).max() / ref_votes.max() < 1e-5
+    assert rel < tol_w, f"node degree off by {rel:.2e}"
+    rel_v = np.abs(gv - ref_votes).max() / ref_votes.max()
+    assert rel_v < tol_w, f"votes off by {rel_v:.2e}"
     # the rho spill (pass 1 keeps the bin positions in HBM, pass 2 streams them back) is only a
     # different route for the same integers: none / partial / complete spill give identical sums
     for tiles in (0, 3):
