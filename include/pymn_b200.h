@@ -123,6 +123,27 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
                   const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
                   const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream);
 
+/* ---- K3, exact form: centroid votes on the int8 tensor cores -----------------
+ * Same product as mn_votes_fast (MetaNeighborUS.py:361-366; MetaNeighbor.py:170-174), computed as integer limb
+ * products with int32 accumulators: the dot product of the cell's integer ranks with the centroid (quantised
+ * to 21 bits of its largest entry) is exact, hence independent of tiling, k order and GPU count.
+ *   mn_limb_split_cells      fp16 planes of K1 -> int8 limb planes a1, a0 [M, ldk] (d = 128 a1 + a0) and the
+ *                            double-precision scale inv_norm64[m] = 1 / ||d_m|| (0 = dropped cell)
+ *   mn_limb_split_centroids  float32 rows [R, ld] -> three stacked int8 limb planes
+ *                            limbs[(l * rows_pad + r) * ldk + g], l = 0 (128^2), 1 (128), 2 (1), with a per-row
+ *                            power-of-two scale: in[r, g] ~= (128^2 b2 + 128 b1 + b0) * inv_scale[r];
+ *                            the caller zero-fills rows R..rows_pad-1
+ *   mn_votes_fast_i8         out[n, m] = float(dot(m, n) * inv_norm64[m] * inv_scale[n] + addend[n]), evaluated in
+ *                            double and rounded once; out float32 column-major [Nn, ldo]
+ * ldk, ldb: row pitch in bytes, multiples of 128 (padding zero); b_limb_rows (= rows_pad): multiple of 128. */
+int mn_limb_split_cells(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t M,
+                        int32_t G, int8_t* a1, int8_t* a0, int64_t ldk, double* inv_norm64, mn_stream_t stream);
+int mn_limb_split_centroids(const float* in, int64_t ld, int32_t R, int32_t G, int8_t* limbs, int64_t ldk,
+                            int64_t rows_pad, float* inv_scale, mn_stream_t stream);
+int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                     const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
+                     const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream);
+
 /* ---- K4/K5: full cell x cell network, never materialised -----------------
  * Replaces create_nw_spearman + rank (utils.py:35-75: np.corrcoef, one ranking
  * of all N^2 entries) and the vote products that consume it

@@ -32,6 +32,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mn {
@@ -43,7 +45,7 @@ constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, eac
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_STAGES = 6;
-constexpr int MAX_TERMS = 4;
+constexpr int MAX_TERMS = 6;
 constexpr int TQ = 4;                     // depth of the tile-index queue of the dynamic scheduler
 
 enum { EPI_STORE = 0, EPI_HIST = 1, EPI_VOTE = 2 };
@@ -54,8 +56,15 @@ struct GemmParams {
     int k_blocks;     // ceil(G / 64)
     int k_last;       // MMA steps (of 16 genes) the last k-block needs: ceil((G - 64 (k_blocks - 1)) / 16)
     int n_terms;      // plane products accumulated into one tile
-    int a_sel[MAX_TERMS];   // 0 = hi plane, 1 = lo plane
-    int b_sel[MAX_TERMS];
+    int a_sel[MAX_TERMS];   // 0 = hi plane, 1 = lo plane          (int8 form: 0 = limb a1, 1 = limb a0)
+    int b_sel[MAX_TERMS];   //                                     (int8 form: 0 / 1 / 2 = limb b2 / b1 / b0)
+    // int8 form (exact integer dot products, mn_votes_fast_i8): every limb product has a weight 128^cls and is
+    // accumulated into the int32 accumulator of its class (the "chain" slots of TMEM); the limb planes of B are
+    // stacked in ONE tensor map, limb l at rows [l * b_limb_rows, ...)
+    int cls[MAX_TERMS];
+    int cls_first[MAX_TERMS];     // 1 = first term of its class: its first MMA overwrites the accumulator
+    int b_limb_rows;
+    const double* inv_a64;        // [M] exact-ish row scale 1/||d|| (double)
     int tri;          // 1: only tiles that contain some column index > row index
     int mt0, mt1;     // row-tile range handled by this launch
     int mt_step;      // ... of which every mt_step-th, starting at mt0 (row tiles dealt round-robin to GPUs)
@@ -202,6 +211,22 @@ __device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc,
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -272,6 +297,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // kind::f16, A=B=F16, D=F32, both K-major
 __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::i8, A=B=signed 8 bit, D=S32, both K-major (K = 32 per instruction)
+__device__ __forceinline__ uint32_t make_idesc_i8(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Position of rho on the bin axis; pass 1 and pass 2 must agree bit for bit.
@@ -512,7 +541,7 @@ struct TileIter {
 // epilogue (four per quarter, a quarter of the columns each; opt-in MN_HIST_EW16).  Measured at config 2:
 // 16 warps are no faster (73.0 vs 70.8 ms), and dropping the histogram atomics altogether changes nothing
 // (72.8 vs 72.9 ms): the epilogue is not what paces pass 1 -- the power cap is.
-template <int BN, int EPI, int NCHAIN, int CTAS, int EW = EPI_WARPS>
+template <int BN, int EPI, int NCHAIN, int CTAS, int EW = EPI_WARPS, int I8 = 0>
 __global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -524,6 +553,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // Correct (same tests) but measured slower than pairs: see corr_ctas().
     constexpr bool PAIR = (CTAS >= 2);
     constexpr bool QUAD = (CTAS == 4);
+    // elements of one k-block along the TMA's K coordinate: 128 bytes either way (64 fp16 / 128 int8)
+    constexpr int BKE = I8 ? 128 : BK;
+    static_assert(!I8 || (EPI == EPI_STORE && NCHAIN == 4), "the int8 form is wired for the vote store epilogue");
     static_assert(CTAS == 1 || CTAS == 2 || CTAS == 4, "1 CTA, a pair, or two pairs");
     constexpr int B_ROWS = BN / (PAIR ? 2 : 1);    // rows of the B tile this CTA stages
     constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -671,23 +703,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 const int m0 = it.mt * (BM * CTAS) + (int)cta_rank * BM, n0 = it.nt() * BN + (int)pair_rank * B_ROWS;
                 for (int term = 0; term < p.n_terms; ++term) {
                     const CUtensorMap* ma = p.a_sel[term] ? &tm_a_lo : &tm_a_hi;
-                    const CUtensorMap* mb = p.b_sel[term] ? &tm_b_lo : &tm_b_hi;
+                    const CUtensorMap* mb = (!I8 && p.b_sel[term]) ? &tm_b_lo : &tm_b_hi;
+                    const int nb0 = I8 ? n0 + p.b_sel[term] * p.b_limb_rows : n0;
                     for (int kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         unsigned char* sa = ring + (size_t)s * STAGE_BYTES;
                         if constexpr (PAIR) {
                             if (pair_leader) mbar_expect_tx(&full_bar[s], STAGE_BYTES * 2);
-                            tma_load_2d_pair(sa, ma, &full_bar[s], kb * BK, m0);
+                            tma_load_2d_pair(sa, ma, &full_bar[s], kb * BKE, m0);
                             if constexpr (QUAD) {      // pair 0 fetches the B half for its own CTA and the one below it
                                 if (cta_rank < 2u)
-                                    tma_load_2d_pair_mc(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0, (uint16_t)(5u << pair_rank));
+                                    tma_load_2d_pair_mc(sa + A_BYTES, mb, &full_bar[s], kb * BKE, nb0, (uint16_t)(5u << pair_rank));
                             } else {
-                                tma_load_2d_pair(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                                tma_load_2d_pair(sa + A_BYTES, mb, &full_bar[s], kb * BKE, nb0);
                             }
                         } else {
                             mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                            tma_load_2d(sa, ma, &full_bar[s], kb * BK, m0);
-                            tma_load_2d(sa + A_BYTES, mb, &full_bar[s], kb * BK, n0);
+                            tma_load_2d(sa, ma, &full_bar[s], kb * BKE, m0);
+                            tma_load_2d(sa + A_BYTES, mb, &full_bar[s], kb * BKE, nb0);
                         }
                         if (++s == p.stages) {
                             s = 0;
@@ -700,7 +733,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0 && pair_leader) {
-            const uint32_t idesc = make_idesc(BM * (PAIR ? 2 : 1), BN);
+            const uint32_t idesc = I8 ? make_idesc_i8(BM * (PAIR ? 2 : 1), BN) : make_idesc(BM * (PAIR ? 2 : 1), BN);
             const uint16_t pair_mask = (uint16_t)(3u << pair_lead);            // the two CTAs of this pair
             const uint16_t slot_mask = QUAD ? (uint16_t)0xF : pair_mask;       // everyone whose producer reuses the slot
             int s = 0, a = 0, qs = 0;
@@ -716,9 +749,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (tile < 0) break;
                 mbar_wait(&tempty_bar[a], aph ^ 1u);
                 tc_fence_after();
-                int kb = 0;
+                int kb = 0, term = 0;
                 for (int i = 0; i < n_iters; ++i) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC_COLS + (i % NCHAIN) * BN);
+                    // fp16 form: k-blocks dealt round-robin to the NCHAIN accumulators; int8 form: accumulator = weight class
+                    const int chain = I8 ? p.cls[term] : (i % NCHAIN);
+                    const bool fresh = I8 ? (kb == 0 && p.cls_first[term] != 0) : (i < NCHAIN);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC_COLS + chain * BN);
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(ring + (size_t)s * STAGE_BYTES);
@@ -727,17 +763,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     // the last k-block of a plane product holds G mod 64 genes (the rest is zero padding):
                     // only the 16-gene steps that carry data are issued (G = 2000: 1 of 4)
                     const int k_steps = (kb == p.k_blocks - 1) ? p.k_last : BK / UMMA_K;
-                    if (++kb == p.k_blocks) kb = 0;
+                    if (++kb == p.k_blocks) {
+                        kb = 0;
+                        ++term;
+                    }
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         if (k >= k_steps) break;
-                        // advance the start address by k * 16 elements * 2 B = 32 B = 2 (16-byte units)
-                        if constexpr (PAIR)
-                            tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                            (i >= NCHAIN || k > 0) ? 1u : 0u);
-                        else
-                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                       (i >= NCHAIN || k > 0) ? 1u : 0u);
+                        // advance the start address by k * 16 elements * 2 B (32 int8) = 32 B = 2 (16-byte units)
+                        const uint32_t accum = (!fresh || k > 0) ? 1u : 0u;
+                        if constexpr (I8) {
+                            if constexpr (PAIR) tc_mma_i8_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                            else tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                        } else {
+                            if constexpr (PAIR) tc_mma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                            else tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                        }
                     }
                     // frees the smem slot (of both CTAs) once these MMAs retire
                     if constexpr (PAIR) tc_commit_pair(&empty_bar[s], slot_mask);
@@ -816,7 +857,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             // quad's first column tile) lies entirely below it -- either way the per-element test decides
             const bool diag_tile = (n0 <= m0 + BM - 1);
 
-            if (EPI == EPI_STORE) {
+            if (EPI == EPI_STORE && I8) {
+                // exact integer dot product: sum over the weight classes, class c scaled by 128^c (Horner, int64)
+                const double inv_i64 = row_ok ? p.inv_a64[m] : 0.0;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
+                    long long v[32];
+                    uint32_t r[32];
+                    tmem_ld32(t_base + (uint32_t)(c0 + 3 * BN), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = (long long)(int)r[c];
+#pragma unroll
+                    for (int cl = 2; cl >= 0; --cl) {
+                        tmem_ld32(t_base + (uint32_t)(c0 + cl * BN), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = v[c] * 128 + (long long)(int)r[c];
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int64_t n = n0 + c0 + c;
+                            if (n < p.N)
+                                p.out[n * p.ldo + m] = (float)fma((double)v[c] * inv_i64, (double)s_invb[c0 + c], (double)s_add[c0 + c]);
+                        }
+                    }
+                }
+            } else if (EPI == EPI_STORE) {
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     uint32_t r[32];
@@ -1224,17 +1292,18 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // rows x cols fp16, row pitch ld elements; box = 64 columns x box_rows rows, 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    bool i8 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
         return 4;
     }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * (i8 ? 1 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(i8 ? 128 : BK), (cuuint32_t)box_rows};      // 128 bytes of K either way
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(map, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1246,14 +1315,10 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
 }
 
 static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
 }
 
 // row tiles per L2 band of the tile schedule: 64 x 128 rows x (G * 2 B) of A = 32 MB at G = 2000, L2-resident
@@ -1292,6 +1357,25 @@ static int corr_ctas(bool wide) {
     return 2;
 }
 
+// Tile counters of the dynamic scheduler: a small rotating pool PER DEVICE (a process may drive several GPUs,
+// and launches on different streams may overlap), handed out under a lock.
+static int next_tile_counter(unsigned int** out) {
+    constexpr int N_COUNTERS = 64, MAX_DEV = 64;
+    static std::mutex mu;
+    static unsigned int* pools[MAX_DEV] = {nullptr};
+    static unsigned int next[MAX_DEV] = {0};
+    int dev = 0;
+    MN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) {
+        set_error("gemm: device ordinal %d out of range", dev);
+        return 6;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) MN_CUDA(cudaMalloc(&pools[dev], N_COUNTERS * sizeof(unsigned int)));
+    *out = pools[dev] + (next[dev]++ % N_COUNTERS);
+    return 0;
+}
+
 template <int BN>
 static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
     int warps = 20;
@@ -1323,22 +1407,26 @@ static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
     return 0;
 }
 
-template <int BN, int EPI, int NCHAIN, int CTAS = 1, int EW = EPI_WARPS>
-static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int64_t M, const __half* b_hi,
-                       const __half* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
+// I8 = 1: a_hi / a_lo are the int8 limb planes a1 / a0 of A (row pitch lda BYTES), b_hi the stacked limb planes of B
+// (3 * p.b_limb_rows rows, row pitch ldb bytes), b_lo unused.
+template <int BN, int EPI, int NCHAIN, int CTAS = 1, int EW = EPI_WARPS, int I8 = 0>
+static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, int64_t M, const void* b_hi,
+                       const void* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     const int64_t cols_a = lda, cols_b = ldb;     // padding columns are zero; beyond ld the TMA zero-fills
     int rc;
-    if ((rc = make_map(&ta_hi, a_hi, M, cols_a, lda, BM))) return rc;
-    if ((rc = make_map(&ta_lo, a_lo ? a_lo : a_hi, M, cols_a, lda, BM))) return rc;
+    if ((rc = make_map(&ta_hi, a_hi, M, cols_a, lda, BM, I8))) return rc;
+    if ((rc = make_map(&ta_lo, a_lo ? a_lo : a_hi, M, cols_a, lda, BM, I8))) return rc;
     constexpr int B_BOX = BN / (CTAS >= 2 ? 2 : 1);      // rows of B one CTA stages (half a tile in the pair forms)
-    if ((rc = make_map(&tb_hi, b_hi, N, cols_b, ldb, B_BOX))) return rc;
-    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, N, cols_b, ldb, B_BOX))) return rc;
+    const int64_t b_rows = I8 ? 3 * (int64_t)p.b_limb_rows : N;
+    if ((rc = make_map(&tb_hi, b_hi, b_rows, cols_b, ldb, B_BOX, I8))) return rc;
+    if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, b_rows, cols_b, ldb, B_BOX, I8))) return rc;
     p.M = M;
     p.N = N;
     p.ctas = CTAS;
-    p.k_blocks = (G + BK - 1) / BK;
-    p.k_last = (G - (p.k_blocks - 1) * BK + UMMA_K - 1) / UMMA_K;
+    constexpr int BKE = I8 ? 128 : BK, KSTEP = I8 ? 32 : UMMA_K;
+    p.k_blocks = (G + BKE - 1) / BKE;
+    p.k_last = (G - (p.k_blocks - 1) * BKE + KSTEP - 1) / KSTEP;
     p.n_tiles = (int)((N + BN - 1) / BN);
     if (p.band <= 0) p.band = gemm_band() / CTAS;
     const size_t stage_bytes = (size_t)(BM + B_BOX) * BK * 2;
@@ -1358,7 +1446,7 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     }
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
-    auto kern = gemm_kernel<BN, EPI, NCHAIN, CTAS, EW>;
+    auto kern = gemm_kernel<BN, EPI, NCHAIN, CTAS, EW, I8>;
     MN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // number of tiles (of BM * CTAS rows)
     long long tiles = 0;
@@ -1369,11 +1457,7 @@ static int launch_gemm(const __half* a_hi, const __half* a_lo, int64_t lda, int6
     grid *= CTAS;
     // dynamic scheduler: one counter per launch out of a small rotating pool (launches on different
     // streams may overlap), zeroed on the launch stream
-    static unsigned int* counters = nullptr;
-    static int next_counter = 0;
-    constexpr int N_COUNTERS = 64;
-    if (!counters) MN_CUDA(cudaMalloc(&counters, N_COUNTERS * sizeof(unsigned int)));
-    p.tile_counter = counters + (next_counter++ % N_COUNTERS);
+    if ((rc = next_tile_counter(&p.tile_counter))) return rc;
     p.total_tiles = (int)tiles;
     MN_CUDA(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), st));
     if (CTAS == 1) {
@@ -1439,6 +1523,42 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
     // BN <= 128 leaves room for 4 accumulator chains in TMEM (accuracy over tile width)
     if (Nn <= 64) return launch_gemm<64, EPI_STORE, 4>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
     return launch_gemm<128, EPI_STORE, 4>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
+}
+
+int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                     const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
+                     const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream) {
+    using namespace mn;
+    MN_CHECK_ARG(a1 && a0 && b_limbs && inv_norm64 && inv_scale && out, "mn_votes_fast_i8: null pointer");
+    MN_CHECK_ARG(M >= 1 && Nn >= 1 && ldo >= M && G >= 1 && G <= 16000, "mn_votes_fast_i8: bad shape (G <= 16000)");
+    MN_CHECK_ARG(lda % 128 == 0 && ldb % 128 == 0 && lda >= G && ldb >= G, "mn_votes_fast_i8: row pitches must be multiples of 128 bytes");
+    MN_CHECK_ARG(b_limb_rows >= Nn && b_limb_rows % 128 == 0, "mn_votes_fast_i8: b_limb_rows must be a multiple of 128 >= Nn");
+    MN_CHECK_ARG(((reinterpret_cast<uintptr_t>(a1) | reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(b_limbs)) & 15) == 0,
+                 "mn_votes_fast_i8: planes must be 16-byte aligned");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    // limb weights: a1 = 128, a0 = 1; b2 = 128^2, b1 = 128, b0 = 1 -> class = exponent of 128 of the product
+    static const int A_SEL[6] = {0, 0, 1, 0, 1, 1}, B_SEL[6] = {0, 1, 0, 2, 1, 2};
+    bool seen[4] = {false, false, false, false};
+    for (int t = 0; t < 6; ++t) {
+        p.a_sel[t] = A_SEL[t];
+        p.b_sel[t] = B_SEL[t];
+        p.cls[t] = (1 - A_SEL[t]) + (2 - B_SEL[t]);
+        p.cls_first[t] = seen[p.cls[t]] ? 0 : 1;
+        seen[p.cls[t]] = true;
+    }
+    p.n_terms = 6;
+    p.b_limb_rows = b_limb_rows;
+    p.tri = 0;
+    p.mt0 = 0;
+    p.mt1 = (int)((M + BM - 1) / BM);
+    p.mt_step = 1;
+    p.inv_a64 = inv_norm64;
+    p.inv_b = inv_scale;
+    p.addend = addend;
+    p.out = out;
+    p.ldo = ldo;
+    return launch_gemm<128, EPI_STORE, 4, 1, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
 }
 
 static int corr_terms(mn::GemmParams& p, bool has_lo) {

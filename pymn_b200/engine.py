@@ -214,6 +214,33 @@ def split_f16(C: torch.Tensor, G: int):
     return hi, lo, inv_scale
 
 
+def cell_limbs(rc: RankedCells):
+    """int8 limb planes of the ranked cells (d = 128 a1 + a0) and their double-precision scale, cached on ``rc``."""
+    if getattr(rc, "_limbs", None) is None:
+        dev = rc.d_hi.device
+        ldk = (rc.G + 127) // 128 * 128
+        a1 = torch.empty((rc.M, ldk), dtype=torch.int8, device=dev)
+        a0 = torch.empty((rc.M, ldk), dtype=torch.int8, device=dev)
+        inv64 = torch.empty((rc.M,), dtype=torch.float64, device=dev)
+        _lib.call("mn_limb_split_cells", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, rc.M, rc.G, a1, a0, ldk, inv64)
+        rc._limbs = (a1, a0, ldk, inv64)
+    return rc._limbs
+
+
+def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int):
+    """K3, exact form (the product path): votes of all cells for the Nn centroid rows of C (float32 [>= Nn, ld])
+    through integer limb products on the int8 tensor cores.  Returns float32 [Nn, M] column-major votes."""
+    dev = rc.d_hi.device
+    a1, a0, ldk, inv64 = cell_limbs(rc)
+    rows_pad = (Nn + 127) // 128 * 128
+    limbs = torch.zeros((3 * rows_pad, ldk), dtype=torch.int8, device=dev)
+    inv_scale = torch.empty((Nn,), dtype=torch.float32, device=dev)
+    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale)
+    out = torch.empty((Nn, rc.M), dtype=torch.float32, device=dev)
+    _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G, out, rc.M)
+    return out
+
+
 def votes_fast(rc: RankedCells, b_hi, b_lo, inv_scale, addend, Nn: int, debug_simt=False):
     """K3.  Returns float32 [Nn, M] (column-major votes: one row per train column)."""
     out = torch.empty((Nn, rc.M), dtype=torch.float32, device=rc.d_hi.device)
@@ -276,9 +303,12 @@ def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_tr
     if n_loc > 0:
         n_b = n_loc + (n_train_studies if ndn else 0)
         if t: t.start("votes_gemm")
-        b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
         addend = n_valid[:n_b].contiguous() if ndn else None
-        out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
+        if _os.environ.get("MN_VOTES_F16"):        # A/B switch: the fp16-plane form (FP32 accumulators)
+            b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
+            out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
+        else:
+            out = votes_exact(rc, C, addend, n_b)
         if t: t.stop("votes_gemm")
         denom = out[n_loc:] if ndn else None
         col_denom = train_study if ndn else None
@@ -812,8 +842,7 @@ def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types:
     vmat = torch.empty((K, rc.M), dtype=torch.float32, device=dev)
     if fast:
         C, n_valid = centroids(rc, ctx.lab_row_off, S * K)
-        b_hi, b_lo, inv_scale = split_f16(C, rc.G)
-        out = votes_fast(rc, b_hi, b_lo, inv_scale, None, S * K)
+        out = votes_exact(rc, C, None, S * K)
         _lib.call("mn_loso_finalize", out, rc.M, 0, None, n_valid, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
         kept = rc.inv_norm > 0
         test_label = torch.where(kept, cell_label, torch.full_like(cell_label, -1))

@@ -148,6 +148,42 @@ def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
                                atol=np.abs(cent).max(axis=1, keepdims=True).max() * 2.0 ** -21)
 
 
+@pytest.mark.parametrize("m,nn,g", [(300, 42, 120), (1000, 200, 2500), (129, 257, 64), (5000, 13, 2000),
+                                    (4097, 128, 333), (700, 1057, 3000), (260, 5, 9000)])
+def test_votes_exact_int8_limbs(eng, m, nn, g):
+    """The int8 limb form (mn_limb_split_* + mn_votes_fast_i8, the product path of the centroid votes): the limb
+    planes reproduce the integers they were split from, and the votes equal the float64 product of the integer
+    ranks with the quantised centroid to float32 rounding -- the integer dot products are exact."""
+    rng = np.random.default_rng(m + nn + g)
+    x = _rand_matrix(rng, m, g, "counts")
+    x[3] = 0                                                     # a dropped cell
+    rc = eng.rank_normalize(eng.to_device(x))
+    cent = rng.normal(size=(nn, g)).astype(np.float32) * rng.uniform(0.01, 50, size=(nn, 1)).astype(np.float32)
+    Cd = torch.zeros((nn + 1, rc.ldd), dtype=torch.float32, device="cuda")
+    Cd[:nn, :g] = eng.to_device(cent)
+    addend = eng.to_device(rng.uniform(0, 100, size=nn).astype(np.float32))
+    out = eng.votes_exact(rc, Cd, addend, nn)
+    torch.cuda.synchronize()
+    a1, a0, ldk, inv64 = eng.cell_limbs(rc)
+    d = _planes(rc, g).astype(np.int64)
+    lim = 128 * a1.cpu().numpy().astype(np.int64) + a0.cpu().numpy().astype(np.int64)
+    assert np.array_equal(lim[:, :g], d) and not lim[:, g:].any(), "limb planes must reproduce the integer ranks"
+    assert a0.cpu().numpy().min() >= -64 and a0.cpu().numpy().max() <= 63
+    ss = (d.astype(np.float64) ** 2).sum(axis=1)
+    inv_ref = np.where(ss > 0, 1.0 / np.sqrt(np.maximum(ss, 1.0)), 0.0)
+    assert np.array_equal(inv64.cpu().numpy(), inv_ref), "double-precision scale from the exact integer norm"
+    # the centroid as the kernel quantises it: 21 bits of the row's largest entry
+    e = np.frexp(np.abs(cent).max(axis=1))[1]
+    sc = np.ldexp(1.0, 20 - e)[:, None]
+    bq = np.rint(cent.astype(np.float64) * sc)
+    ref = (d.astype(np.float64) @ bq.T) * inv_ref[:, None] / sc.T + addend.cpu().numpy().astype(np.float64)[None, :]
+    got = out.cpu().numpy().T
+    assert np.array_equal(got, ref.astype(np.float32)), \
+        f"exact path off by {np.abs(got - ref).max():.3e} (values up to {np.abs(ref).max():.3e})"
+    # and the quantisation is 2^-21 of the row maximum
+    assert np.abs(bq / sc - cent).max() <= np.abs(cent).max() * 2.0 ** -20
+
+
 @pytest.mark.parametrize("n_seg,seg_n,ncols,n_labels,ties", [
     (1, 1000, 5, 4, False), (3, 2500, 9, 12, True), (2, 9000, 3, 6, False), (1, 37, 2, 2, True), (2, 5000, 4, 300, True),
 ])
