@@ -94,9 +94,11 @@ int mn_gene_stats(const float* X, int64_t ldx, const int32_t* row_index, const i
  * Cells are sorted by label: label l owns rows [row_off[l], row_off[l+1]).
  *   centroids  float32 [L, ldc]  (row l = sum over the label's kept cells of d*inv_norm)
  *   n_valid    float32 [L]       number of kept cells (inv_norm > 0) per label
+ *   inv_norm64 double [M] or NULL: the cells' scale in double (mn_limb_split_cells); with it every term is the
+ *              exact integer rank times the double scale and only the final float32 store rounds
  */
 int mn_centroids(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
-                 const int32_t* row_off, int32_t L, int32_t G, float* centroids, int64_t ldc,
+                 const double* inv_norm64, const int32_t* row_off, int32_t L, int32_t G, float* centroids, int64_t ldc,
                  float* n_valid, mn_stream_t stream);
 
 /* out[g_out, :] = sum over rows r with group[r] == g_out of in[r, :]   (rows with group < 0 skipped).
@@ -127,22 +129,40 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  * Same product as mn_votes_fast (MetaNeighborUS.py:361-366; MetaNeighbor.py:170-174), computed as integer limb
  * products with int32 accumulators: the dot product of the cell's integer ranks with the centroid (quantised
  * to 21 bits of its largest entry) is exact, hence independent of tiling, k order and GPU count.
- *   mn_limb_split_cells      fp16 planes of K1 -> int8 limb planes a1, a0 [M, ldk] (d = 128 a1 + a0) and the
+ *   mn_limb_split_cells      fp16 planes of K1 -> int8 limb planes a1, a0 [M, ldk] (d = 128 a1 + a0; G <= 127:
+ *                            a1 = d, a0 = 0) and the
  *                            double-precision scale inv_norm64[m] = 1 / ||d_m|| (0 = dropped cell)
  *   mn_limb_split_centroids  float32 rows [R, ld] -> three stacked int8 limb planes
- *                            limbs[(l * rows_pad + r) * ldk + g], l = 0 (128^2), 1 (128), 2 (1), with a per-row
- *                            power-of-two scale: in[r, g] ~= (128^2 b2 + 128 b1 + b0) * inv_scale[r];
- *                            the caller zero-fills rows R..rows_pad-1
- *   mn_votes_fast_i8         out[n, m] = float(dot(m, n) * inv_norm64[m] * inv_scale[n] + addend[n]), evaluated in
- *                            double and rounded once; out float32 column-major [Nn, ldo]
+ *                            limbs[(l * rows_pad + r) * ldk + g], l = 0 .. 3 (weights 128^3 .. 1), with a per-row
+ *                            power-of-two scale: in[r, g] ~= (128^3 b3 + 128^2 b2 + 128 b1 + b0) * inv_scale[r]
+ *                            (28 bits of the row's largest entry); the caller zero-fills rows R..rows_pad-1
+ *   mn_votes_den64           den[s, m] = inv_norm64[m] * sum_g d[m, g] * C[s, g] + addend[s] in double, for the few
+ *                            study-centroid rows (node degree, MetaNeighborUS.py:363-366); C float32 [S, ldc]
+ *   mn_votes_fast_i8         val = dot(m, n) * inv_norm64[m] * inv_scale[n] + addend[n], evaluated in double;
+ *                            G <= 127 (one digit per rank): dot = the exact integer product; beyond, dot = the
+ *                            exact product minus the weight-1 digit cross term sum_g a0 b0 (four accumulators
+ *                            fit TMEM): a zero-mean sum, ~3e-7 of the product at G = 128, ~3e-9 at G = 3,000;
+ *                            den != NULL: val = val / den[col_den[n] * ld_den + m] * col_scale[n] - 1 -- the
+ *                              node-degree ratio (MetaNeighborUS.py:365-371) taken in double and CENTRED on a
+ *                              per-column reference ratio 1 / col_scale[n] (any positive constant: a monotone
+ *                              map per column, to which the AUROC is invariant), so that the single float32
+ *                              rounding of the result resolves ~1e-9 of the ratio where the cells crowd;
+ *                            den == NULL: val = val - col_scale[n] (NULL = 0);
+ *                            out64 != NULL: val stored as double [Nn, ldo] (the denominators themselves),
+ *                            else rounded once into out, float32 column-major [Nn, ldo]
  * ldk, ldb: row pitch in bytes, multiples of 128 (padding zero); b_limb_rows (= rows_pad): multiple of 128. */
 int mn_limb_split_cells(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t M,
                         int32_t G, int8_t* a1, int8_t* a0, int64_t ldk, double* inv_norm64, mn_stream_t stream);
 int mn_limb_split_centroids(const float* in, int64_t ld, int32_t R, int32_t G, int8_t* limbs, int64_t ldk,
                             int64_t rows_pad, float* inv_scale, mn_stream_t stream);
+int mn_votes_den64(const int8_t* a1, const int8_t* a0, int64_t ldk, const double* inv_norm64, int64_t M, int32_t G,
+                   const float* C, int64_t ldc, const float* addend, int32_t S, double* out, int64_t ldo,
+                   mn_stream_t stream);
 int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
                      const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
-                     const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream);
+                     const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
+                     const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
+                     mn_stream_t stream);
 
 /* ---- K4/K5: full cell x cell network, never materialised -----------------
  * Replaces create_nw_spearman + rank (utils.py:35-75: np.corrcoef, one ranking

@@ -26,13 +26,15 @@ SIGNATURES = {
     "mn_rank_normalize": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mn_rank_normalize_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mn_gene_stats": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "mn_centroids": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "mn_centroids": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "mn_group_sum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "mn_split_f16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "mn_votes_fast": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "mn_limb_split_cells": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
     "mn_limb_split_centroids": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i64, _vp, _vp]),
-    "mn_votes_fast_i8": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "mn_votes_den64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "mn_votes_fast_i8": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i64,
+                                   _vp, _i64, _vp, _vp, _vp]),
     "mn_corr_hist": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mn_corr_spill_layout": (C.c_int, [_i64, _i64, _i64, _i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
     "mn_corr_lut": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),

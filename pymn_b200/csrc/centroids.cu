@@ -14,7 +14,8 @@ namespace mn {
 // grid (ceil(ldc/2/T), L); each thread owns two adjacent genes, walks the
 // label's rows in order, accumulates in double.
 __global__ void centroid_kernel(const __half* __restrict__ d_hi, const __half* __restrict__ d_lo, int64_t ldd,
-                                const float* __restrict__ inv_norm, const int32_t* __restrict__ row_off, int G,
+                                const float* __restrict__ inv_norm, const double* __restrict__ inv_norm64,
+                                const int32_t* __restrict__ row_off, int G,
                                 float* __restrict__ out, int64_t ldc, float* __restrict__ n_valid) {
     const int l = blockIdx.y;
     const int g2 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,8 +41,14 @@ __global__ void centroid_kernel(const __half* __restrict__ d_hi, const __half* _
             v.x += u.x;   // exact: |d| < 2^15
             v.y += u.y;
         }
-        a0 += (double)(v.x * w);   // one fp32 rounding per term, like the float matrix of the reference path
-        a1 += (double)(v.y * w);
+        if (inv_norm64) {          // exact integers times the double-precision scale: only the final store rounds
+            const double w64 = inv_norm64[r];
+            a0 = fma((double)v.x, w64, a0);
+            a1 = fma((double)v.y, w64, a1);
+        } else {
+            a0 += (double)(v.x * w);   // one fp32 rounding per term
+            a1 += (double)(v.y * w);
+        }
     }
     out[(int64_t)l * ldc + g] = (float)a0;
     if (g + 1 < G) out[(int64_t)l * ldc + g + 1] = (float)a1;
@@ -163,15 +170,15 @@ __global__ void loso_finalize_kernel(const void* __restrict__ in, int64_t ldi, i
 extern "C" {
 
 int mn_centroids(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm,
-                 const int32_t* row_off, int32_t L, int32_t G, float* centroids, int64_t ldc, float* n_valid,
+                 const double* inv_norm64, const int32_t* row_off, int32_t L, int32_t G, float* centroids, int64_t ldc, float* n_valid,
                  mn_stream_t stream) {
     MN_CHECK_ARG(d_hi && inv_norm && row_off && centroids && n_valid, "mn_centroids: null pointer");
     MN_CHECK_ARG(L >= 1 && G >= 1 && ldc >= G && (ldd % 2) == 0, "mn_centroids: bad shape");
     const int T = 128;
     dim3 grid((unsigned)((G + 2 * T - 1) / (2 * T)), (unsigned)L);
     mn::centroid_kernel<<<grid, T, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(d_hi), reinterpret_cast<const __half*>(d_lo), ldd, inv_norm, row_off, G,
-        centroids, ldc, n_valid);
+        reinterpret_cast<const __half*>(d_hi), reinterpret_cast<const __half*>(d_lo), ldd, inv_norm, inv_norm64, row_off,
+        G, centroids, ldc, n_valid);
     MN_LAUNCH_CHECK();
     return 0;
 }

@@ -45,7 +45,7 @@ constexpr int EPI_WARPS = 8;             // two warps per TMEM lane quarter, eac
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int MAX_STAGES = 6;
-constexpr int MAX_TERMS = 6;
+constexpr int MAX_TERMS = 8;
 constexpr int TQ = 4;                     // depth of the tile-index queue of the dynamic scheduler
 
 enum { EPI_STORE = 0, EPI_HIST = 1, EPI_VOTE = 2 };
@@ -57,14 +57,24 @@ struct GemmParams {
     int k_last;       // MMA steps (of 16 genes) the last k-block needs: ceil((G - 64 (k_blocks - 1)) / 16)
     int n_terms;      // plane products accumulated into one tile
     int a_sel[MAX_TERMS];   // 0 = hi plane, 1 = lo plane          (int8 form: 0 = limb a1, 1 = limb a0)
-    int b_sel[MAX_TERMS];   //                                     (int8 form: 0 / 1 / 2 = limb b2 / b1 / b0)
+    int b_sel[MAX_TERMS];   //                                     (int8 form: 0 .. 3 = limb b3 .. b0)
     // int8 form (exact integer dot products, mn_votes_fast_i8): every limb product has a weight 128^cls and is
     // accumulated into the int32 accumulator of its class (the "chain" slots of TMEM); the limb planes of B are
     // stacked in ONE tensor map, limb l at rows [l * b_limb_rows, ...)
     int cls[MAX_TERMS];
     int cls_first[MAX_TERMS];     // 1 = first term of its class: its first MMA overwrites the accumulator
     int b_limb_rows;
+    int cls_mul;                  // weight of accumulator slot 0 (128 with two limbs of A, 1 with one)
     const double* inv_a64;        // [M] exact-ish row scale 1/||d|| (double)
+    // ... its epilogue, all in double:  val = dot * inv_a64[m] * inv_b[n] + addend[n];
+    //   den != null:  val = val / den[col_den[n] * ld_den + m] * col_scale[n] - 1     (node-degree ratio, centred)
+    //   else       :  val = val - col_scale[n]                                         (col_scale may be null = 0)
+    //   out64 != null: val is stored as double there, else rounded once to float32 in out
+    double* out64;
+    const double* den;
+    int64_t ld_den;
+    const int32_t* col_den;
+    const double* col_scale;
     int tri;          // 1: only tiles that contain some column index > row index
     int mt0, mt1;     // row-tile range handled by this launch
     int mt_step;      // ... of which every mt_step-th, starting at mt0 (row tiles dealt round-robin to GPUs)
@@ -836,6 +846,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (EPI == EPI_VOTE && !(ib > 0.f)) ib = __int_as_float(0x7fc00000);   // dropped / absent column: NaN
                 s_invb[c] = ib;
                 if (EPI == EPI_STORE) s_add[c] = (ok && p.addend) ? p.addend[n] : 0.f;
+                if (EPI == EPI_STORE && I8) {
+                    s_lab[c] = (ok && p.den) ? p.col_den[n] : 0;
+                    reinterpret_cast<double*>(s_colw)[c] = (ok && p.col_scale) ? p.col_scale[n] : (p.den ? 1.0 : 0.0);
+                }
                 if (EPI == EPI_VOTE) {
                     const int lab = ok ? p.label[n] : 0;
                     s_lab[c] = lab;
@@ -858,7 +872,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
             const bool diag_tile = (n0 <= m0 + BM - 1);
 
             if (EPI == EPI_STORE && I8) {
-                // exact integer dot product: sum over the weight classes, class c scaled by 128^c (Horner, int64)
+                // exact integer dot product: sum over the weight classes, class c scaled by 128^(c+1) (Horner, int64)
                 const double inv_i64 = row_ok ? p.inv_a64[m] : 0.0;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
@@ -875,12 +889,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
 #pragma unroll
                         for (int c = 0; c < 32; ++c) v[c] = v[c] * 128 + (long long)(int)r[c];
                     }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] *= p.cls_mul;
                     if (row_ok) {
+                        const double* s_scale64 = reinterpret_cast<const double*>(s_colw);
+                        int last_sd = -1;
+                        double rden = 1.0;
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const int64_t n = n0 + c0 + c;
-                            if (n < p.N)
-                                p.out[n * p.ldo + m] = (float)fma((double)v[c] * inv_i64, (double)s_invb[c0 + c], (double)s_add[c0 + c]);
+                            if (n < p.N) {
+                                double val = fma((double)v[c] * inv_i64, (double)s_invb[c0 + c], (double)s_add[c0 + c]);
+                                if (p.den) {
+                                    // the denominator depends on (cell, train study) only: one reciprocal per run of
+                                    // columns of one study (warp-uniform branch: all lanes work on the same column)
+                                    const int sd = s_lab[c0 + c];
+                                    if (sd != last_sd) {
+                                        last_sd = sd;
+                                        rden = 1.0 / p.den[(int64_t)sd * p.ld_den + m];
+                                    }
+                                    val = fma(val * rden, s_scale64[c0 + c], -1.0);
+                                } else {
+                                    val -= s_scale64[c0 + c];
+                                }
+                                if (p.out64) p.out64[n * p.ldo + m] = val;
+                                else p.out[n * p.ldo + m] = (float)val;
+                            }
                         }
                     }
                 }
@@ -1408,7 +1442,7 @@ static int launch_vote_spill(const GemmParams& p, cudaStream_t st) {
 }
 
 // I8 = 1: a_hi / a_lo are the int8 limb planes a1 / a0 of A (row pitch lda BYTES), b_hi the stacked limb planes of B
-// (3 * p.b_limb_rows rows, row pitch ldb bytes), b_lo unused.
+// (4 * p.b_limb_rows rows, row pitch ldb bytes), b_lo unused.
 template <int BN, int EPI, int NCHAIN, int CTAS = 1, int EW = EPI_WARPS, int I8 = 0>
 static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, int64_t M, const void* b_hi,
                        const void* b_lo, int64_t ldb, int64_t N, int G, GemmParams p, cudaStream_t st) {
@@ -1418,7 +1452,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, int64_t 
     if ((rc = make_map(&ta_hi, a_hi, M, cols_a, lda, BM, I8))) return rc;
     if ((rc = make_map(&ta_lo, a_lo ? a_lo : a_hi, M, cols_a, lda, BM, I8))) return rc;
     constexpr int B_BOX = BN / (CTAS >= 2 ? 2 : 1);      // rows of B one CTA stages (half a tile in the pair forms)
-    const int64_t b_rows = I8 ? 3 * (int64_t)p.b_limb_rows : N;
+    const int64_t b_rows = I8 ? 4 * (int64_t)p.b_limb_rows : N;
     if ((rc = make_map(&tb_hi, b_hi, b_rows, cols_b, ldb, B_BOX, I8))) return rc;
     if ((rc = make_map(&tb_lo, b_lo ? b_lo : b_hi, b_rows, cols_b, ldb, B_BOX, I8))) return rc;
     p.M = M;
@@ -1527,9 +1561,12 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
 
 int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
                      const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
-                     const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream) {
+                     const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
+                     const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
+                     mn_stream_t stream) {
     using namespace mn;
-    MN_CHECK_ARG(a1 && a0 && b_limbs && inv_norm64 && inv_scale && out, "mn_votes_fast_i8: null pointer");
+    MN_CHECK_ARG(a1 && a0 && b_limbs && inv_norm64 && inv_scale && (out || out64), "mn_votes_fast_i8: null pointer");
+    MN_CHECK_ARG(!den || (col_den && ld_den >= M), "mn_votes_fast_i8: den needs col_den and ld_den >= M");
     MN_CHECK_ARG(M >= 1 && Nn >= 1 && ldo >= M && G >= 1 && G <= 16000, "mn_votes_fast_i8: bad shape (G <= 16000)");
     MN_CHECK_ARG(lda % 128 == 0 && ldb % 128 == 0 && lda >= G && ldb >= G, "mn_votes_fast_i8: row pitches must be multiples of 128 bytes");
     MN_CHECK_ARG(b_limb_rows >= Nn && b_limb_rows % 128 == 0, "mn_votes_fast_i8: b_limb_rows must be a multiple of 128 >= Nn");
@@ -1537,17 +1574,33 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
                  "mn_votes_fast_i8: planes must be 16-byte aligned");
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    // limb weights: a1 = 128, a0 = 1; b2 = 128^2, b1 = 128, b0 = 1 -> class = exponent of 128 of the product
-    static const int A_SEL[6] = {0, 0, 1, 0, 1, 1}, B_SEL[6] = {0, 1, 0, 2, 1, 2};
     bool seen[4] = {false, false, false, false};
-    for (int t = 0; t < 6; ++t) {
-        p.a_sel[t] = A_SEL[t];
-        p.b_sel[t] = B_SEL[t];
-        p.cls[t] = (1 - A_SEL[t]) + (2 - B_SEL[t]);
-        p.cls_first[t] = seen[p.cls[t]] ? 0 : 1;
-        seen[p.cls[t]] = true;
+    if (G <= 127) {
+        // one limb of A (a1 = d itself, weight 1): the four products a1 * b3 .. b0 are the whole dot product
+        for (int t = 0; t < 4; ++t) {
+            p.a_sel[t] = 0;
+            p.b_sel[t] = t;
+            p.cls[t] = 3 - t;
+            p.cls_first[t] = 1;
+        }
+        p.n_terms = 4;
+        p.cls_mul = 1;
+    } else {
+        // limb weights: a1 = 128, a0 = 1; b3 .. b0 = 128^3 .. 1 -> class = exponent of 128 of the product, 1 .. 4
+        // (accumulator slot = class - 1).  The weight-1 product a0 * b0 is NOT formed: TMEM holds four 128-column
+        // accumulators.  sum_g a0 b0 is a zero-mean sum of G products of balanced 7-bit digits, ~1,400-2,400 sqrt(G),
+        // against a dot product of ~2^25 G^2: 3e-7 of it at G = 128, 3e-9 at G = 3,000 (include/pymn_b200.h).
+        static const int A_SEL[7] = {0, 0, 1, 0, 1, 0, 1}, B_SEL[7] = {0, 1, 0, 2, 1, 3, 2};
+        for (int t = 0; t < 7; ++t) {
+            p.a_sel[t] = A_SEL[t];
+            p.b_sel[t] = B_SEL[t];
+            p.cls[t] = (1 - A_SEL[t]) + (3 - B_SEL[t]) - 1;
+            p.cls_first[t] = seen[p.cls[t]] ? 0 : 1;
+            seen[p.cls[t]] = true;
+        }
+        p.n_terms = 7;
+        p.cls_mul = 128;
     }
-    p.n_terms = 6;
     p.b_limb_rows = b_limb_rows;
     p.tri = 0;
     p.mt0 = 0;
@@ -1557,6 +1610,11 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
     p.inv_b = inv_scale;
     p.addend = addend;
     p.out = out;
+    p.out64 = out64;
+    p.den = den;
+    p.ld_den = ld_den;
+    p.col_den = col_den;
+    p.col_scale = col_scale;
     p.ldo = ldo;
     return launch_gemm<128, EPI_STORE, 4, 1, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
 }

@@ -6,8 +6,10 @@
 // per study.  Splitting both operands into signed base-128 limbs makes every limb product an int8 MMA with an
 // int32 accumulator: the dot product of the integer ranks with the centroid, quantised to 21 bits of its
 // largest entry, is EXACT, independent of tile shape, k order and GPU count.
-//   cell      d = 128 a1 + a0,              a0 in [-64, 63], |a1| <= 127   (G <= 16,000)
-//   centroid  b = rint(c * 2^s) = 128^2 b2 + 128 b1 + b0,  b0 in [-64, 63], b1, b2 in [-64, 64]
+//   cell      d = 128 a1 + a0,              a0 in [-64, 63], |a1| <= 127   (G <= 16,000);  G <= 127: a1 = d, a0 = 0
+//   centroid  b = rint(c * 2^s) = 128^3 b3 + 128^2 b2 + 128 b1 + b0,  b0 in [-64, 63], b1 .. b3 in [-64, 64]
+// 28 bits of the centroid's largest entry: measured on the config-4-shaped fixture (7 x 5,000 cells, 700 clusters)
+// 21 bits cost up to 3 rank flips per AUROC cell, 24 bits 2, 28 bits 1 (and 0.002 on average).
 #include "common.cuh"
 
 namespace mn {
@@ -21,6 +23,7 @@ limb_split_cells_kernel(const __half* __restrict__ d_hi, const __half* __restric
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * LS_WARPS;
+    const bool one_limb = G <= 127;          // |d| < G fits one digit: the products with a0 vanish
     for (int64_t row = warp0; row < M; row += n_warps) {
         const __half* ph = d_hi + row * ldd;
         const __half* pl = d_lo ? d_lo + row * ldd : nullptr;
@@ -49,8 +52,8 @@ limb_split_cells_kernel(const __half* __restrict__ d_hi, const __half* __restric
             uint32_t w1 = 0u, w0 = 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int hi = (d[u] + 64) >> 7;                 // floor((d + 64) / 128)
-                const int lo = d[u] - (hi << 7);                 // [-64, 63]
+                const int hi = one_limb ? d[u] : (d[u] + 64) >> 7;      // floor((d + 64) / 128)
+                const int lo = one_limb ? 0 : d[u] - (hi << 7);         // [-64, 63]
                 w1 |= ((uint32_t)hi & 0xffu) << (8 * u);
                 w0 |= ((uint32_t)lo & 0xffu) << (8 * u);
                 ss += (unsigned long long)((long long)d[u] * d[u]);
@@ -63,7 +66,7 @@ limb_split_cells_kernel(const __half* __restrict__ d_hi, const __half* __restric
     }
 }
 
-// one CTA per centroid row: power-of-two scale so that max|v| * scale is in [2^19, 2^20), then three limbs
+// one CTA per centroid row: power-of-two scale so that max|v| * scale is in [2^26, 2^27), then four limbs
 __global__ void limb_split_centroids_kernel(const float* __restrict__ in, int64_t ld, int G, int8_t* __restrict__ limbs,
                                             int64_t ldk, int64_t rows_pad, float* __restrict__ inv_scale) {
     __shared__ float s_red[32];
@@ -90,31 +93,104 @@ __global__ void limb_split_centroids_kernel(const float* __restrict__ in, int64_
     if (m > 0.f) {
         int e;
         frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)
-        sc = ldexpf(1.f, 20 - e);      // m * sc in [2^19, 2^20)
+        sc = ldexpf(1.f, 27 - e);      // m * sc in [2^26, 2^27)
     }
     if (threadIdx.x == 0) inv_scale[r] = 1.f / sc;   // exact: sc is a power of two
-    int8_t* p2 = limbs + ((int64_t)0 * rows_pad + r) * ldk;
-    int8_t* p1 = limbs + ((int64_t)1 * rows_pad + r) * ldk;
-    int8_t* p0 = limbs + ((int64_t)2 * rows_pad + r) * ldk;
+    int8_t* p3 = limbs + ((int64_t)0 * rows_pad + r) * ldk;
+    int8_t* p2 = limbs + ((int64_t)1 * rows_pad + r) * ldk;
+    int8_t* p1 = limbs + ((int64_t)2 * rows_pad + r) * ldk;
+    int8_t* p0 = limbs + ((int64_t)3 * rows_pad + r) * ldk;
     for (int g = threadIdx.x; g < (int)ldk; g += blockDim.x) {
         int b = 0;
         if (g < G) {
-            const float v = x[g] * sc;                        // exact (power-of-two scale)
-            b = (v == v) ? __float2int_rn(fminf(fmaxf(v, -1048576.f), 1048576.f)) : 0;
+            const float v = x[g] * sc;                        // exact (power-of-two scale); |v| < 2^27, 24-bit mantissa
+            b = (v == v) ? __float2int_rn(fminf(fmaxf(v, -134217728.f), 134217728.f)) : 0;
         }
-        const int b2 = (b + 8192) >> 14;                      // [-64, 64]
-        const int rem = b - (b2 << 14);                       // [-8192, 8191]
+        const int b3 = (b + (1 << 20)) >> 21;                 // [-64, 64]
+        const int r3 = b - (b3 << 21);                        // [-2^20, 2^20)
+        const int b2 = (r3 + 8192) >> 14;                     // [-64, 64]
+        const int rem = r3 - (b2 << 14);                      // [-8192, 8191]
         const int b1 = (rem + 64) >> 7;                       // [-64, 64]
         const int b0 = rem - (b1 << 7);                       // [-64, 63]
+        p3[g] = (int8_t)b3;
         p2[g] = (int8_t)b2;
         p1[g] = (int8_t)b1;
         p0[g] = (int8_t)b0;
     }
 }
 
+// Node degree in double: den[s, m] = inv_norm64[m] * sum_g d[m, g] * C[s, g] + addend[s]  (MetaNeighborUS.py:363-366).
+// One warp per cell; every lane owns 4 genes per step and SB running sums.  The products d * C are exact in
+// double (14 x 24 bits), the sum carries ~1e-13.  S <= a few studies: 2 S G FMAs per cell, hidden under the
+// 2 G bytes of limbs the cell streams in.
+template <int SB>
+__global__ void __launch_bounds__(LS_WARPS * 32)
+votes_den64_kernel(const int8_t* __restrict__ a1, const int8_t* __restrict__ a0, int64_t ldk,
+                   const double* __restrict__ inv_norm64, int64_t M, int G, const float* __restrict__ C, int64_t ldc,
+                   const float* __restrict__ addend, int s0, int S, double* __restrict__ out, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * LS_WARPS;
+    const int ns = (S - s0) < SB ? (S - s0) : SB;
+    for (int64_t row = warp0; row < M; row += n_warps) {
+        double acc[SB];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) acc[q] = 0.0;
+        for (int g0 = lane * 4; g0 < G; g0 += 128) {
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(a1 + row * ldk + g0);
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(a0 + row * ldk + g0);
+            double d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                d[u] = (double)((G <= 127 ? 1 : 128) * (int)(int8_t)(w1 >> (8 * u)) + (int)(int8_t)(w0 >> (8 * u)));   // 0 beyond G (padding)
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                if (q < ns) {
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(C + (int64_t)(s0 + q) * ldc + g0));
+                    acc[q] = fma(d[0], (double)c.x, acc[q]);
+                    acc[q] = fma(d[1], (double)c.y, acc[q]);
+                    acc[q] = fma(d[2], (double)c.z, acc[q]);
+                    acc[q] = fma(d[3], (double)c.w, acc[q]);
+                }
+            }
+        }
+        const double w = inv_norm64[row];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+            const double t = warp_sum(acc[q]);
+            if (lane == 0 && q < ns) out[(int64_t)(s0 + q) * ldo + row] = fma(t, w, addend ? (double)addend[s0 + q] : 0.0);
+        }
+    }
+}
+
 }  // namespace mn
 
 extern "C" {
+
+int mn_votes_den64(const int8_t* a1, const int8_t* a0, int64_t ldk, const double* inv_norm64, int64_t M, int32_t G,
+                   const float* C, int64_t ldc, const float* addend, int32_t S, double* out, int64_t ldo,
+                   mn_stream_t stream) {
+    MN_CHECK_ARG(a1 && a0 && inv_norm64 && C && out, "mn_votes_den64: null pointer");
+    MN_CHECK_ARG(M >= 1 && G >= 1 && S >= 1 && ldo >= M && ldk % 128 == 0 && ldk >= G, "mn_votes_den64: bad shape");
+    MN_CHECK_ARG(ldc % 4 == 0 && ldc >= ((G + 3) / 4) * 4 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                 "mn_votes_den64: centroid rows must be 16-byte aligned, zero-padded to a multiple of 4 genes");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (M + mn::LS_WARPS - 1) / mn::LS_WARPS;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s0 = 0; s0 < S; s0 += 8) {
+        if (S - s0 <= 4)
+            mn::votes_den64_kernel<4><<<(unsigned)blocks, mn::LS_WARPS * 32, 0, st>>>(a1, a0, ldk, inv_norm64, M, G, C, ldc,
+                                                                                 addend, s0, S, out, ldo);
+        else
+            mn::votes_den64_kernel<8><<<(unsigned)blocks, mn::LS_WARPS * 32, 0, st>>>(a1, a0, ldk, inv_norm64, M, G, C, ldc,
+                                                                                 addend, s0, S, out, ldo);
+        MN_LAUNCH_CHECK();
+    }
+    return 0;
+}
 
 int mn_limb_split_cells(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t M,
                         int32_t G, int8_t* a1, int8_t* a0, int64_t ldk, double* inv_norm64, mn_stream_t stream) {

@@ -191,10 +191,12 @@ def gene_stats(X, perm: np.ndarray, seg_off: np.ndarray):
 
 
 def centroids(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: int = 0):
-    """K2.  Returns (C float32 [L + extra_rows, ldd] (extra rows zero), n_valid float32 [L + extra_rows])."""
+    """K2.  Returns (C float32 [L + extra_rows, ldd] (extra rows zero), n_valid float32 [L + extra_rows]).
+    The terms are the exact integer ranks times the cells' double-precision scale (cell_limbs)."""
     C = torch.zeros((L + extra_rows, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)
     n_valid = torch.zeros((L + extra_rows,), dtype=torch.float32, device=rc.d_hi.device)
-    _lib.call("mn_centroids", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, row_off, L, rc.G, C, rc.ldd, n_valid)
+    inv64 = cell_limbs(rc)[3]
+    _lib.call("mn_centroids", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, inv64, row_off, L, rc.G, C, rc.ldd, n_valid)
     return C, n_valid
 
 
@@ -227,17 +229,30 @@ def cell_limbs(rc: RankedCells):
     return rc._limbs
 
 
-def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int):
+def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col_den=None, col_scale=None,
+                as_double=False):
     """K3, exact form (the product path): votes of all cells for the Nn centroid rows of C (float32 [>= Nn, ld])
-    through integer limb products on the int8 tensor cores.  Returns float32 [Nn, M] column-major votes."""
+    through integer limb products on the int8 tensor cores; the epilogue works in double:
+    val = x.c + addend;  with ``den`` (double [S, M]) val = val / den[col_den[n]] * col_scale[n] - 1, otherwise
+    val -= col_scale[n].  Returns [Nn, M] column-major, float32 (rounded once) or float64 (``as_double``)."""
     dev = rc.d_hi.device
     a1, a0, ldk, inv64 = cell_limbs(rc)
     rows_pad = (Nn + 127) // 128 * 128
-    limbs = torch.zeros((3 * rows_pad, ldk), dtype=torch.int8, device=dev)
+    limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
     inv_scale = torch.empty((Nn,), dtype=torch.float32, device=dev)
     _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale)
-    out = torch.empty((Nn, rc.M), dtype=torch.float32, device=dev)
-    _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G, out, rc.M)
+    out = torch.empty((Nn, rc.M), dtype=torch.float64 if as_double else torch.float32, device=dev)
+    _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G,
+              None if as_double else out, out if as_double else None, rc.M,
+              den, int(den.stride(0)) if den is not None else 0, col_den, col_scale)
+    return out
+
+
+def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int):
+    """Node degree of every cell against the S study-centroid rows of C, in double: [S, M]."""
+    a1, a0, ldk, inv64 = cell_limbs(rc)
+    out = torch.empty((S, rc.M), dtype=torch.float64, device=rc.d_hi.device)
+    _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, C, int(C.stride(0)), addend, S, out, rc.M)
     return out
 
 
@@ -307,11 +322,29 @@ def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_tr
         if _os.environ.get("MN_VOTES_F16"):        # A/B switch: the fp16-plane form (FP32 accumulators)
             b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
             out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
+            denom = out[n_loc:] if ndn else None
+            col_denom = train_study if ndn else None
         else:
-            out = votes_exact(rc, C, addend, n_b)
+            # Exact integer dot products; the node-degree ratio is taken in double inside the epilogue and centred
+            # on a per-column reference so that its one float32 rounding resolves ~1e-9 of the ratio where the
+            # cells crowd (rounding numerator and denominator to float32 first costs 3-4 rank flips per AUROC
+            # cell at 5,000 cells per study).  Reference = the column's mean vote over a block of cells: any
+            # positive constant is a monotone map of the column, to which K6 / K7 are invariant.
+            m0 = min(rc.M, 16384)
+            Cs, ns = centroids(rc, torch.tensor([0, m0], dtype=torch.int32, device=dev), 1)
+            mu = ((C[:n_b] * Cs[0]).sum(dim=1) / ns[0].clamp(min=1.0)).double()
+            if ndn:
+                num_ref = mu[:n_loc] + addend[:n_loc].double()
+                den_ref = (mu[n_loc:] + addend[n_loc:].double()).index_select(0, train_study.long())
+                ref = num_ref / den_ref
+                scale = torch.where(torch.isfinite(ref) & (ref > 0), 1.0 / ref, torch.ones_like(ref)).contiguous()
+                den64 = votes_den64(rc, C[n_loc:n_b], addend[n_loc:n_b].contiguous(), n_train_studies)
+                out = votes_exact(rc, C, addend[:n_loc].contiguous(), n_loc, den=den64, col_den=train_study,
+                                  col_scale=scale)
+            else:
+                out = votes_exact(rc, C, None, n_loc, col_scale=mu[:n_loc].contiguous())
+            denom = col_denom = None
         if t: t.stop("votes_gemm")
-        denom = out[n_loc:] if ndn else None
-        col_denom = train_study if ndn else None
         if t: t.start("auroc")
         auc, n_pos = auroc(out, n_loc, denom, col_denom, seg_off, n_seg, cell_label, n_lab)
         if t: t.stop("auroc")

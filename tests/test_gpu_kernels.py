@@ -149,7 +149,7 @@ def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
 
 
 @pytest.mark.parametrize("m,nn,g", [(300, 42, 120), (1000, 200, 2500), (129, 257, 64), (5000, 13, 2000),
-                                    (4097, 128, 333), (700, 1057, 3000), (260, 5, 9000)])
+                                    (4097, 128, 333), (700, 1057, 3000), (260, 5, 9000), (900, 30, 127)])
 def test_votes_exact_int8_limbs(eng, m, nn, g):
     """The int8 limb form (mn_limb_split_* + mn_votes_fast_i8, the product path of the centroid votes): the limb
     planes reproduce the integers they were split from, and the votes equal the float64 product of the integer
@@ -166,22 +166,38 @@ def test_votes_exact_int8_limbs(eng, m, nn, g):
     torch.cuda.synchronize()
     a1, a0, ldk, inv64 = eng.cell_limbs(rc)
     d = _planes(rc, g).astype(np.int64)
-    lim = 128 * a1.cpu().numpy().astype(np.int64) + a0.cpu().numpy().astype(np.int64)
+    lim = (128 if g > 127 else 1) * a1.cpu().numpy().astype(np.int64) + a0.cpu().numpy().astype(np.int64)
     assert np.array_equal(lim[:, :g], d) and not lim[:, g:].any(), "limb planes must reproduce the integer ranks"
     assert a0.cpu().numpy().min() >= -64 and a0.cpu().numpy().max() <= 63
     ss = (d.astype(np.float64) ** 2).sum(axis=1)
     inv_ref = np.where(ss > 0, 1.0 / np.sqrt(np.maximum(ss, 1.0)), 0.0)
     assert np.array_equal(inv64.cpu().numpy(), inv_ref), "double-precision scale from the exact integer norm"
-    # the centroid as the kernel quantises it: 21 bits of the row's largest entry
+    # the centroid as the kernel quantises it: 28 bits of the row's largest entry, in balanced base-128 digits;
+    # the weight-1 cross term of the lowest digits of both operands is the one product that is not formed
     e = np.frexp(np.abs(cent).max(axis=1))[1]
-    sc = np.ldexp(1.0, 20 - e)[:, None]
-    bq = np.rint(cent.astype(np.float64) * sc)
-    ref = (d.astype(np.float64) @ bq.T) * inv_ref[:, None] / sc.T + addend.cpu().numpy().astype(np.float64)[None, :]
+    sc = np.ldexp(1.0, 27 - e)[:, None]
+    bq = np.rint(cent.astype(np.float64) * sc).astype(np.int64)
+    a0_ = ((d + 64) % 128) - 64 if g > 127 else np.zeros_like(d)
+    b0_ = ((bq + 64) % 128) - 64
+    dot = d @ bq.T - a0_ @ b0_.T
+    ref = dot.astype(np.float64) * inv_ref[:, None] / sc.T + addend.cpu().numpy().astype(np.float64)[None, :]
     got = out.cpu().numpy().T
     assert np.array_equal(got, ref.astype(np.float32)), \
         f"exact path off by {np.abs(got - ref).max():.3e} (values up to {np.abs(ref).max():.3e})"
-    # and the quantisation is 2^-21 of the row maximum
-    assert np.abs(bq / sc - cent).max() <= np.abs(cent).max() * 2.0 ** -20
+    assert np.abs(bq / sc - cent).max() <= np.abs(cent).max() * 2.0 ** -27
+    assert np.abs(a0_ @ b0_.T).max() <= 6.0 * 4096.0 * np.sqrt(g), "the digit product that is not formed is a zero-mean sum"
+    # node degree in double (mn_votes_den64) and the centred ratio of the epilogue
+    S = min(nn, 3)
+    den = eng.votes_den64(rc, Cd[:S], addend[:S].contiguous(), S)
+    den_ref = (d.astype(np.float64) @ cent[:S].astype(np.float64).T) * inv_ref[:, None] + addend.cpu().numpy().astype(np.float64)[None, :S]
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(den.cpu().numpy().T, den_ref, rtol=1e-12, atol=1e-12 * np.abs(den_ref).max())
+    col_den = eng._i32((np.arange(nn) % S).astype(np.int32))
+    scale = eng.to_device(rng.uniform(0.5, 2.0, size=nn))
+    rat = eng.votes_exact(rc, Cd, addend, nn, den=den, col_den=col_den, col_scale=scale)
+    torch.cuda.synchronize()
+    want = ref / den.cpu().numpy().T[:, np.arange(nn) % S] * scale.cpu().numpy()[None, :] - 1.0
+    np.testing.assert_allclose(rat.cpu().numpy().T, want.astype(np.float32), rtol=2e-7, atol=2e-7)
 
 
 @pytest.mark.parametrize("n_seg,seg_n,ncols,n_labels,ties", [
