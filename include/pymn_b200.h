@@ -136,8 +136,11 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
  *                            limbs[(l * rows_pad + r) * ldk + g], l = 0 .. 3 (weights 128^3 .. 1), with a per-row
  *                            power-of-two scale: in[r, g] ~= (128^3 b3 + 128^2 b2 + 128 b1 + b0) * inv_scale[r]
  *                            (28 bits of the row's largest entry); the caller zero-fills rows R..rows_pad-1
- *   mn_votes_den64           den[s, m] = inv_norm64[m] * sum_g d[m, g] * C[s, g] + addend[s] in double, for the few
- *                            study-centroid rows (node degree, MetaNeighborUS.py:363-366); C float32 [S, ldc]
+ *                            q32 (optional): the same 28-bit integers as one int32 plane [R, ldk]
+ *                            (limbs may be NULL when only q32 is wanted)
+ *   mn_votes_den64           den[s, m] = inv_norm64[m] * inv_scale[s] * sum_g d[m, g] * q32[s, g] + addend[s] for the
+ *                            few study-centroid rows (node degree, MetaNeighborUS.py:363-366): exact 64-bit
+ *                            integer dot products on the CUDA cores, scaled in double
  *   mn_votes_fast_i8         val = dot(m, n) * inv_norm64[m] * inv_scale[n] + addend[n], evaluated in double;
  *                            G <= 127 (one digit per rank): dot = the exact integer product; beyond, dot = the
  *                            exact product minus the weight-1 digit cross term sum_g a0 b0 (four accumulators
@@ -154,10 +157,10 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
 int mn_limb_split_cells(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const float* inv_norm, int64_t M,
                         int32_t G, int8_t* a1, int8_t* a0, int64_t ldk, double* inv_norm64, mn_stream_t stream);
 int mn_limb_split_centroids(const float* in, int64_t ld, int32_t R, int32_t G, int8_t* limbs, int64_t ldk,
-                            int64_t rows_pad, float* inv_scale, mn_stream_t stream);
+                            int64_t rows_pad, float* inv_scale, int32_t* q32, mn_stream_t stream);
 int mn_votes_den64(const int8_t* a1, const int8_t* a0, int64_t ldk, const double* inv_norm64, int64_t M, int32_t G,
-                   const float* C, int64_t ldc, const float* addend, int32_t S, double* out, int64_t ldo,
-                   mn_stream_t stream);
+                   const int32_t* q32, const float* inv_scale, const float* addend, int32_t S, double* out,
+                   int64_t ldo, mn_stream_t stream);
 int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
                      const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
                      const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,

@@ -31,8 +31,8 @@ SIGNATURES = {
     "mn_split_f16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "mn_votes_fast": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "mn_limb_split_cells": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
-    "mn_limb_split_centroids": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i64, _vp, _vp]),
-    "mn_votes_den64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "mn_limb_split_centroids": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "mn_votes_den64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "mn_votes_fast_i8": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i64,
                                    _vp, _i64, _vp, _vp, _vp]),
     "mn_corr_hist": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),

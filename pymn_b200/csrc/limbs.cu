@@ -68,7 +68,8 @@ limb_split_cells_kernel(const __half* __restrict__ d_hi, const __half* __restric
 
 // one CTA per centroid row: power-of-two scale so that max|v| * scale is in [2^26, 2^27), then four limbs
 __global__ void limb_split_centroids_kernel(const float* __restrict__ in, int64_t ld, int G, int8_t* __restrict__ limbs,
-                                            int64_t ldk, int64_t rows_pad, float* __restrict__ inv_scale) {
+                                            int64_t ldk, int64_t rows_pad, float* __restrict__ inv_scale,
+                                            int32_t* __restrict__ q32) {
     __shared__ float s_red[32];
     const int r = blockIdx.x;
     const float* x = in + (int64_t)r * ld;
@@ -96,10 +97,10 @@ __global__ void limb_split_centroids_kernel(const float* __restrict__ in, int64_
         sc = ldexpf(1.f, 27 - e);      // m * sc in [2^26, 2^27)
     }
     if (threadIdx.x == 0) inv_scale[r] = 1.f / sc;   // exact: sc is a power of two
-    int8_t* p3 = limbs + ((int64_t)0 * rows_pad + r) * ldk;
-    int8_t* p2 = limbs + ((int64_t)1 * rows_pad + r) * ldk;
-    int8_t* p1 = limbs + ((int64_t)2 * rows_pad + r) * ldk;
-    int8_t* p0 = limbs + ((int64_t)3 * rows_pad + r) * ldk;
+    int8_t* p3 = limbs ? limbs + ((int64_t)0 * rows_pad + r) * ldk : nullptr;
+    int8_t* p2 = limbs ? limbs + ((int64_t)1 * rows_pad + r) * ldk : nullptr;
+    int8_t* p1 = limbs ? limbs + ((int64_t)2 * rows_pad + r) * ldk : nullptr;
+    int8_t* p0 = limbs ? limbs + ((int64_t)3 * rows_pad + r) * ldk : nullptr;
     for (int g = threadIdx.x; g < (int)ldk; g += blockDim.x) {
         int b = 0;
         if (g < G) {
@@ -112,53 +113,61 @@ __global__ void limb_split_centroids_kernel(const float* __restrict__ in, int64_
         const int rem = r3 - (b2 << 14);                      // [-8192, 8191]
         const int b1 = (rem + 64) >> 7;                       // [-64, 64]
         const int b0 = rem - (b1 << 7);                       // [-64, 63]
-        p3[g] = (int8_t)b3;
-        p2[g] = (int8_t)b2;
-        p1[g] = (int8_t)b1;
-        p0[g] = (int8_t)b0;
+        if (q32) q32[(int64_t)r * ldk + g] = b;
+        if (limbs) {
+            p3[g] = (int8_t)b3;
+            p2[g] = (int8_t)b2;
+            p1[g] = (int8_t)b1;
+            p0[g] = (int8_t)b0;
+        }
     }
 }
 
-// Node degree in double: den[s, m] = inv_norm64[m] * sum_g d[m, g] * C[s, g] + addend[s]  (MetaNeighborUS.py:363-366).
-// One warp per cell; every lane owns 4 genes per step and SB running sums.  The products d * C are exact in
-// double (14 x 24 bits), the sum carries ~1e-13.  S <= a few studies: 2 S G FMAs per cell, hidden under the
-// 2 G bytes of limbs the cell streams in.
+// Node degree in double: den[s, m] = inv_norm64[m] * inv_scale[s] * sum_g d[m, g] * q[s, g] + addend[s]
+// (MetaNeighborUS.py:363-366), q = the study centroid quantised to 28 bits exactly as the limb planes are
+// (limb_split_centroids_kernel's q32 plane).  One warp per cell; every lane owns 4 genes per step and SB running
+// 64-bit integer sums (one IMAD.WIDE per product: exact, and no int->double conversions in the loop).
+// S is a handful of studies: 2 S G integer FMAs per cell, hidden under the 2 G bytes of limbs the cell streams in.
 template <int SB>
 __global__ void __launch_bounds__(LS_WARPS * 32)
 votes_den64_kernel(const int8_t* __restrict__ a1, const int8_t* __restrict__ a0, int64_t ldk,
-                   const double* __restrict__ inv_norm64, int64_t M, int G, const float* __restrict__ C, int64_t ldc,
-                   const float* __restrict__ addend, int s0, int S, double* __restrict__ out, int64_t ldo) {
+                   const double* __restrict__ inv_norm64, int64_t M, int G, const int32_t* __restrict__ q32,
+                   const float* __restrict__ inv_scale, const float* __restrict__ addend, int s0, int S,
+                   double* __restrict__ out, int64_t ldo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * LS_WARPS;
     const int ns = (S - s0) < SB ? (S - s0) : SB;
+    const int w1mul = G <= 127 ? 1 : 128;
     for (int64_t row = warp0; row < M; row += n_warps) {
-        double acc[SB];
+        long long acc[SB];
 #pragma unroll
-        for (int q = 0; q < SB; ++q) acc[q] = 0.0;
+        for (int q = 0; q < SB; ++q) acc[q] = 0;
         for (int g0 = lane * 4; g0 < G; g0 += 128) {
             const uint32_t w1 = *reinterpret_cast<const uint32_t*>(a1 + row * ldk + g0);
             const uint32_t w0 = *reinterpret_cast<const uint32_t*>(a0 + row * ldk + g0);
-            double d[4];
+            int d[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                d[u] = (double)((G <= 127 ? 1 : 128) * (int)(int8_t)(w1 >> (8 * u)) + (int)(int8_t)(w0 >> (8 * u)));   // 0 beyond G (padding)
+                d[u] = w1mul * (int)(int8_t)(w1 >> (8 * u)) + (int)(int8_t)(w0 >> (8 * u));   // 0 beyond G (padding)
 #pragma unroll
             for (int q = 0; q < SB; ++q) {
                 if (q < ns) {
-                    const float4 c = __ldg(reinterpret_cast<const float4*>(C + (int64_t)(s0 + q) * ldc + g0));
-                    acc[q] = fma(d[0], (double)c.x, acc[q]);
-                    acc[q] = fma(d[1], (double)c.y, acc[q]);
-                    acc[q] = fma(d[2], (double)c.z, acc[q]);
-                    acc[q] = fma(d[3], (double)c.w, acc[q]);
+                    const int4 c = __ldg(reinterpret_cast<const int4*>(q32 + (int64_t)(s0 + q) * ldk + g0));
+                    acc[q] += (long long)d[0] * c.x;
+                    acc[q] += (long long)d[1] * c.y;
+                    acc[q] += (long long)d[2] * c.z;
+                    acc[q] += (long long)d[3] * c.w;
                 }
             }
         }
         const double w = inv_norm64[row];
 #pragma unroll
         for (int q = 0; q < SB; ++q) {
-            const double t = warp_sum(acc[q]);
-            if (lane == 0 && q < ns) out[(int64_t)(s0 + q) * ldo + row] = fma(t, w, addend ? (double)addend[s0 + q] : 0.0);
+            const long long t = warp_sum(acc[q]);
+            if (lane == 0 && q < ns)
+                out[(int64_t)(s0 + q) * ldo + row] =
+                    fma((double)t * w, (double)inv_scale[s0 + q], addend ? (double)addend[s0 + q] : 0.0);
         }
     }
 }
@@ -168,12 +177,11 @@ votes_den64_kernel(const int8_t* __restrict__ a1, const int8_t* __restrict__ a0,
 extern "C" {
 
 int mn_votes_den64(const int8_t* a1, const int8_t* a0, int64_t ldk, const double* inv_norm64, int64_t M, int32_t G,
-                   const float* C, int64_t ldc, const float* addend, int32_t S, double* out, int64_t ldo,
+                   const int32_t* q32, const float* inv_scale, const float* addend, int32_t S, double* out, int64_t ldo,
                    mn_stream_t stream) {
-    MN_CHECK_ARG(a1 && a0 && inv_norm64 && C && out, "mn_votes_den64: null pointer");
+    MN_CHECK_ARG(a1 && a0 && inv_norm64 && q32 && inv_scale && out, "mn_votes_den64: null pointer");
     MN_CHECK_ARG(M >= 1 && G >= 1 && S >= 1 && ldo >= M && ldk % 128 == 0 && ldk >= G, "mn_votes_den64: bad shape");
-    MN_CHECK_ARG(ldc % 4 == 0 && ldc >= ((G + 3) / 4) * 4 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
-                 "mn_votes_den64: centroid rows must be 16-byte aligned, zero-padded to a multiple of 4 genes");
+    MN_CHECK_ARG((reinterpret_cast<uintptr_t>(q32) & 15) == 0, "mn_votes_den64: q32 must be 16-byte aligned");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -182,11 +190,11 @@ int mn_votes_den64(const int8_t* a1, const int8_t* a0, int64_t ldk, const double
     cudaStream_t st = (cudaStream_t)stream;
     for (int s0 = 0; s0 < S; s0 += 8) {
         if (S - s0 <= 4)
-            mn::votes_den64_kernel<4><<<(unsigned)blocks, mn::LS_WARPS * 32, 0, st>>>(a1, a0, ldk, inv_norm64, M, G, C, ldc,
-                                                                                 addend, s0, S, out, ldo);
+            mn::votes_den64_kernel<4><<<(unsigned)blocks, mn::LS_WARPS * 32, 0, st>>>(a1, a0, ldk, inv_norm64, M, G, q32,
+                                                                                 inv_scale, addend, s0, S, out, ldo);
         else
-            mn::votes_den64_kernel<8><<<(unsigned)blocks, mn::LS_WARPS * 32, 0, st>>>(a1, a0, ldk, inv_norm64, M, G, C, ldc,
-                                                                                 addend, s0, S, out, ldo);
+            mn::votes_den64_kernel<8><<<(unsigned)blocks, mn::LS_WARPS * 32, 0, st>>>(a1, a0, ldk, inv_norm64, M, G, q32,
+                                                                                 inv_scale, addend, s0, S, out, ldo);
         MN_LAUNCH_CHECK();
     }
     return 0;
@@ -211,10 +219,10 @@ int mn_limb_split_cells(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ld
 }
 
 int mn_limb_split_centroids(const float* in, int64_t ld, int32_t R, int32_t G, int8_t* limbs, int64_t ldk,
-                            int64_t rows_pad, float* inv_scale, mn_stream_t stream) {
-    MN_CHECK_ARG(in && limbs && inv_scale && R >= 1 && G >= 1 && ld >= G, "mn_limb_split_centroids: bad arguments");
+                            int64_t rows_pad, float* inv_scale, int32_t* q32, mn_stream_t stream) {
+    MN_CHECK_ARG(in && (limbs || q32) && inv_scale && R >= 1 && G >= 1 && ld >= G, "mn_limb_split_centroids: bad arguments");
     MN_CHECK_ARG(ldk % 128 == 0 && ldk >= G && rows_pad >= R, "mn_limb_split_centroids: bad plane shape");
-    mn::limb_split_centroids_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(in, ld, G, limbs, ldk, rows_pad, inv_scale);
+    mn::limb_split_centroids_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(in, ld, G, limbs, ldk, rows_pad, inv_scale, q32);
     MN_LAUNCH_CHECK();
     return 0;
 }

@@ -240,7 +240,7 @@ def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col
     rows_pad = (Nn + 127) // 128 * 128
     limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
     inv_scale = torch.empty((Nn,), dtype=torch.float32, device=dev)
-    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale)
+    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale, None)
     out = torch.empty((Nn, rc.M), dtype=torch.float64 if as_double else torch.float32, device=dev)
     _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G,
               None if as_double else out, out if as_double else None, rc.M,
@@ -250,9 +250,13 @@ def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col
 
 def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int):
     """Node degree of every cell against the S study-centroid rows of C, in double: [S, M]."""
+    dev = rc.d_hi.device
     a1, a0, ldk, inv64 = cell_limbs(rc)
-    out = torch.empty((S, rc.M), dtype=torch.float64, device=rc.d_hi.device)
-    _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, C, int(C.stride(0)), addend, S, out, rc.M)
+    q32 = torch.empty((S, ldk), dtype=torch.int32, device=dev)
+    inv_scale = torch.empty((S,), dtype=torch.float32, device=dev)
+    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), S, rc.G, None, ldk, S, inv_scale, q32)
+    out = torch.empty((S, rc.M), dtype=torch.float64, device=dev)
+    _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, q32, inv_scale, addend, S, out, rc.M)
     return out
 
 
@@ -330,9 +334,11 @@ def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_tr
             # cells crowd (rounding numerator and denominator to float32 first costs 3-4 rank flips per AUROC
             # cell at 5,000 cells per study).  Reference = the column's mean vote over a block of cells: any
             # positive constant is a monotone map of the column, to which K6 / K7 are invariant.
-            m0 = min(rc.M, 16384)
-            Cs, ns = centroids(rc, torch.tensor([0, m0], dtype=torch.int32, device=dev), 1)
-            mu = ((C[:n_b] * Cs[0]).sum(dim=1) / ns[0].clamp(min=1.0)).double()
+            m0 = min(rc.M, 4096)               # (as 32-cell pseudo-labels: K2 walks a label's rows serially)
+            nb = max(1, m0 // 32)
+            Cs, ns = centroids(rc, torch.arange(0, 32 * nb + 1, 32, dtype=torch.int32, device=dev)
+                               if m0 >= 32 else torch.tensor([0, m0], dtype=torch.int32, device=dev), nb)
+            mu = ((C[:n_b] * Cs.sum(dim=0)).sum(dim=1) / ns.sum().clamp(min=1.0)).double()
             if ndn:
                 num_ref = mu[:n_loc] + addend[:n_loc].double()
                 den_ref = (mu[n_loc:] + addend[n_loc:].double()).index_select(0, train_study.long())

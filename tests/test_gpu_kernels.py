@@ -189,9 +189,9 @@ def test_votes_exact_int8_limbs(eng, m, nn, g):
     # node degree in double (mn_votes_den64) and the centred ratio of the epilogue
     S = min(nn, 3)
     den = eng.votes_den64(rc, Cd[:S], addend[:S].contiguous(), S)
-    den_ref = (d.astype(np.float64) @ cent[:S].astype(np.float64).T) * inv_ref[:, None] + addend.cpu().numpy().astype(np.float64)[None, :S]
+    den_ref = (d @ bq[:S].T).astype(np.float64) * inv_ref[:, None] / sc.T[:, :S] + addend.cpu().numpy().astype(np.float64)[None, :S]
     torch.cuda.synchronize()
-    np.testing.assert_allclose(den.cpu().numpy().T, den_ref, rtol=1e-12, atol=1e-12 * np.abs(den_ref).max())
+    assert np.array_equal(den.cpu().numpy().T, den_ref), "node degree: exact integer dot products, scaled in double"
     col_den = eng._i32((np.arange(nn) % S).astype(np.int32))
     scale = eng.to_device(rng.uniform(0.5, 2.0, size=nn))
     rat = eng.votes_exact(rc, Cd, addend, nn, den=den, col_den=col_den, col_scale=scale)
