@@ -272,13 +272,6 @@ int mn_one_vs_best(const float* votes, int64_t ldv, int32_t ncols, const float* 
                    const int32_t* lab_row_off, const int32_t* cell_label, int32_t n_labels,
                    const double* auroc, double* out, mn_stream_t stream);
 
-/* ---- debug / test-only -----------------------------------------------------
- * Plain CUDA-core GEMM with the same contract as mn_votes_fast; used by the
- * tests to cross-check the tcgen05 kernel on device.  Not on any product path. */
-int mn_debug_votes_simt(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,
-                        const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
-                        const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

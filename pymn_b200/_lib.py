@@ -44,7 +44,6 @@ SIGNATURES = {
     "mn_auroc_workspace_bytes": (_i64, [_i32, _i64, _i32, _i32]),
     "mn_auroc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp]),
     "mn_one_vs_best": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
-    "mn_debug_votes_simt": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -127,14 +127,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
         "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     return ok != 0;
 }
-// Spin until the barrier phase with the given parity completes.  A wait that lasts
-// longer than ~10 s of SM clocks can only be a protocol bug: trap instead of hanging the GPU.
+// Spin until the barrier phase with the given parity completes.  A wait of more than 2^30 polls (each
+// try_wait suspends the thread for a hardware-bounded time: tens of seconds in all) can only be a protocol bug:
+// trap instead of hanging the GPU.  Polls are counted, not clock cycles, so that time spent preempted
+// (time-slicing, a debugger) never trips it.
+constexpr uint32_t MBAR_SPIN_LIMIT = 1u << 30;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait(addr, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(addr, parity)) {
-        if (clock64() - t0 > 20000000000ll) {
+        if (++spins > MBAR_SPIN_LIMIT) {
             printf("pymn_b200 gemm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
             __trap();
         }
@@ -181,9 +184,9 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t addr, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     if (mbar_try_wait_cluster(addr, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait_cluster(addr, parity)) {
-        if (clock64() - t0 > 20000000000ll) {
+        if (++spins > MBAR_SPIN_LIMIT) {
             printf("pymn_b200 gemm: cluster mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
             __trap();
         }
@@ -1289,25 +1292,6 @@ __global__ void vote_rowsum_kernel(const unsigned long long* __restrict__ votes,
     degree[i] = s;
 }
 
-// ------------------------------------------------------------------ debug reference (CUDA cores)
-__global__ void debug_votes_simt_kernel(const __half* a_hi, const __half* a_lo, int64_t lda, const float* inv_norm,
-                                        int64_t M, const __half* b_hi, const __half* b_lo, int64_t ldb,
-                                        const float* inv_scale, const float* addend, int Nn, int G, float* out,
-                                        int64_t ldo) {
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = blockIdx.y;
-    if (m >= M || n >= Nn) return;
-    double acc = 0.0;
-    for (int g = 0; g < G; ++g) {
-        double a = (double)__half2float(a_hi[m * lda + g]);
-        if (a_lo) a += (double)__half2float(a_lo[m * lda + g]);
-        double b = (double)__half2float(b_hi[(int64_t)n * ldb + g]);
-        if (b_lo) b += (double)__half2float(b_lo[(int64_t)n * ldb + g]);
-        acc += a * b;
-    }
-    out[(int64_t)n * ldo + m] = (float)(acc * (double)inv_norm[m] * (double)inv_scale[n] + (addend ? (double)addend[n] : 0.0));
-}
-
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1756,19 +1740,6 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     if (rc) return rc;
     // node degree = sum of a cell's votes over all labels (every voter carries a label)
     vote_rowsum_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p.votes, N, L, p.degree);
-    MN_LAUNCH_CHECK();
-    return 0;
-}
-
-int mn_debug_votes_simt(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, const float* inv_norm, int64_t M,
-                        const mn_half_t* b_hi, const mn_half_t* b_lo, int64_t ldb, const float* inv_scale,
-                        const float* addend, int32_t Nn, int32_t G, float* out, int64_t ldo, mn_stream_t stream) {
-    MN_CHECK_ARG(a_hi && b_hi && inv_norm && inv_scale && out, "mn_debug_votes_simt: null pointer");
-    dim3 grid((unsigned)((M + 127) / 128), (unsigned)Nn);
-    mn::debug_votes_simt_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __half*>(a_hi), reinterpret_cast<const __half*>(a_lo), lda, inv_norm, M,
-        reinterpret_cast<const __half*>(b_hi), reinterpret_cast<const __half*>(b_lo), ldb, inv_scale, addend, Nn, G,
-        out, ldo);
     MN_LAUNCH_CHECK();
     return 0;
 }

@@ -185,11 +185,7 @@ extern "C" int mn_gene_stats(const float* X, int64_t ldx, const int32_t* row_ind
     using namespace mn;
     MN_CHECK_ARG(X && seg_off && median && variance && n_seg >= 1 && G >= 1 && ldx >= G, "mn_gene_stats: bad arguments");
     const size_t smem = (size_t)2 * 256 * GS_GENES * 4 + (size_t)2 * GS_WARPS * GS_GENES * 8 + 4 * GS_GENES * 4;
-    static bool configured = false;
-    if (!configured) {
-        MN_CUDA(cudaFuncSetAttribute(gene_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    MN_CUDA(cudaFuncSetAttribute(gene_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((G + GS_GENES - 1) / GS_GENES), (unsigned)n_seg);
     gene_stats_kernel<<<grid, GS_THREADS, smem, (cudaStream_t)stream>>>(X, ldx, row_index, seg_off, G, median, variance);
     MN_LAUNCH_CHECK();

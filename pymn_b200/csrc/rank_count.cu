@@ -237,11 +237,9 @@ int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, con
     }
     const size_t per_warp = (size_t)RC_HB * 2 + (size_t)g_pad * 2;
     const size_t smem = per_warp * RC_WARPS;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
+    // (set on every launch: the attribute is per device and per context, and the call costs about a microsecond)
+    if (smem > 40 * 1024)
         MN_CUDA(cudaFuncSetAttribute(rank_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -216,11 +216,9 @@ static int rank_dispatch(const float* X, int64_t ldx, mn::CsrIn csr, const int32
     const size_t smem = (size_t)Pmax * 8 + (size_t)G * 4;
     int T = 256;
     if (G <= 64) T = 32; else if (G <= 256) T = 64; else if (G <= 1024) T = 128;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
+    // (set on every launch: the attribute is per device and per context, and the call costs about a microsecond)
+    if (smem > 40 * 1024)
         MN_CUDA(cudaFuncSetAttribute(mn::rank_normalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     int64_t grid = M < (int64_t)(1 << 30) ? M : (int64_t)(1 << 30);
     if (only_overflow && grid > 1184) grid = 1184;      // a small persistent grid scans the flags for the few dense rows
     mn::rank_normalize_kernel<<<(unsigned)grid, T, smem, (cudaStream_t)stream>>>(

@@ -301,11 +301,9 @@ int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, cons
     const size_t per_warp = (size_t)cap * 8 + (size_t)g_pad * 2;
     const size_t smem = per_warp * RW_WARPS;
     *may_overflow = G > cap;
-    static size_t configured = 0;
-    if (smem > 40 * 1024 && smem > configured) {
+    // (set on every launch: the attribute is per device and per context, and the call costs about a microsecond)
+    if (smem > 40 * 1024)
         MN_CUDA(cudaFuncSetAttribute(rank_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

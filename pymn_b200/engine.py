@@ -260,11 +260,10 @@ def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int):
     return out
 
 
-def votes_fast(rc: RankedCells, b_hi, b_lo, inv_scale, addend, Nn: int, debug_simt=False):
+def votes_fast(rc: RankedCells, b_hi, b_lo, inv_scale, addend, Nn: int):
     """K3.  Returns float32 [Nn, M] (column-major votes: one row per train column)."""
     out = torch.empty((Nn, rc.M), dtype=torch.float32, device=rc.d_hi.device)
-    name = "mn_debug_votes_simt" if debug_simt else "mn_votes_fast"
-    _lib.call(name, rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, rc.M, b_hi, b_lo, int(b_hi.stride(0)), inv_scale,
+    _lib.call("mn_votes_fast", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, rc.M, b_hi, b_lo, int(b_hi.stride(0)), inv_scale,
               addend, Nn, rc.G, out, rc.M)
     return out
 

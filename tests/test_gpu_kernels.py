@@ -121,7 +121,7 @@ def test_centroids_and_group_sum(eng, n, g, L):
 @pytest.mark.parametrize("m,nn,g", [(300, 42, 120), (1000, 200, 2500), (129, 257, 64), (5000, 13, 2000),
                                     (4097, 128, 333)])
 def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
-    """tcgen05 GEMM vs float64 NumPy on the very same fp16 planes, and vs the CUDA-core debug kernel."""
+    """tcgen05 GEMM vs float64 NumPy on the very same fp16 planes."""
     rng = np.random.default_rng(m + nn + g)
     x = _rand_matrix(rng, m, g, "counts")
     rc = eng.rank_normalize(eng.to_device(x))
@@ -131,7 +131,6 @@ def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
     b_hi, b_lo, inv_scale = eng.split_f16(Cd, g)
     addend = eng.to_device(rng.uniform(0, 100, size=nn).astype(np.float32))
     out = eng.votes_fast(rc, b_hi, b_lo, inv_scale, addend, nn)
-    dbg = eng.votes_fast(rc, b_hi, b_lo, inv_scale, addend, nn, debug_simt=True)
     torch.cuda.synchronize()
     a = _planes(rc, g)
     b = (b_hi.cpu().numpy().astype(np.float64) + b_lo.cpu().numpy().astype(np.float64))[:, :g]
@@ -139,7 +138,6 @@ def test_votes_fast_tcgen05_vs_reference(eng, m, nn, g):
     ref = ref + addend.cpu().numpy().astype(np.float64)[None, :]
     got = out.cpu().numpy().T.astype(np.float64)
     scale = np.abs(ref - addend.cpu().numpy()[None, :]).max() + 1e-30
-    assert np.abs(dbg.cpu().numpy().T - ref).max() / scale < 1e-6
     err = np.abs(got - ref).max() / scale
     # FP32 accumulation of K ~ 2-3k exact products: IEEE sequential summation would give ~sqrt(K)*2^-24 = 3e-6
     assert err < 4e-6, f"tcgen05 votes differ: rel err {err:.3e}"
