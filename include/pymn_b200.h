@@ -101,6 +101,22 @@ int mn_centroids(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
                  const double* inv_norm64, const int32_t* row_off, int32_t L, int32_t G, float* centroids, int64_t ldc,
                  float* n_valid, mn_stream_t stream);
 
+/* Fixed-point form of mn_centroids (the product path): every term d * inv_norm64 is rounded once to a multiple
+ * of 2^-38 and summed as a 64-bit integer, so the sums are exact, independent of the order of the cells, of the
+ * launch geometry and of how the cells are dealt to GPUs (partial sums of different ranks add with an integer
+ * all-reduce): every world size sees bit-identical centroids.
+ *   cq [L, ldc] int64, nq [L] int32: ACCUMULATED into (the caller zero-fills them once)
+ *   max_label_rows: the largest label's row count (sizes the row slices per label; 0 = one slice)
+ * mn_group_sum_fixed: the study centroids / study sizes as integer sums of label rows (n_in / n_out may be NULL)
+ * mn_centroids_finish: float32 centroids = cq * 2^-38, n_valid = (float)nq, for rows [0, R) */
+int mn_centroids_fixed(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const double* inv_norm64,
+                       const int32_t* row_off, int32_t L, int32_t G, int64_t max_label_rows, int64_t* cq, int64_t ldc,
+                       int32_t* nq, mn_stream_t stream);
+int mn_group_sum_fixed(const int64_t* in, int64_t ld, int32_t R, int32_t width, const int32_t* group, int32_t n_groups,
+                       int64_t* out, const int32_t* n_in, int32_t* n_out, mn_stream_t stream);
+int mn_centroids_finish(const int64_t* cq, const int32_t* nq, int32_t R, int64_t ld, float* centroids, float* n_valid,
+                        mn_stream_t stream);
+
 /* out[g_out, :] = sum over rows r with group[r] == g_out of in[r, :]   (rows with group < 0 skipped).
  * Replaces cluster_centroids @ study_matrix and n_cells_per_cluster @ study_matrix
  * (MetaNeighborUS.py:349-350).  in/out float32 [R, ld] / [n_groups, ld]; width = columns used. */
@@ -225,6 +241,14 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
  * ndn != 0 divides by the node degree (MetaNeighborUS.py:167-169). */
 int mn_votes_finalize(const uint64_t* votes, const uint64_t* degree, const int32_t* label, int64_t N,
                       int32_t L, int32_t ndn, float* out, int64_t ldo, mn_stream_t stream);
+
+/* Test labels of the centroid paths: out_label[i] = cell_label[i], or -1 for a dropped cell (inv_norm[i] == 0:
+ * zero-variance cells leave the ranking, MetaNeighborUS.py:273-281; score_low_mem drops cells whose sum is <= 0,
+ * MetaNeighbor.py:121).  poison (optional, one byte, set to 1, never cleared): some cell is constant but NON-ZERO
+ * (K1 flag bit 0 without bit 1) -- in score_low_mem such a cell normalises to a NaN row that turns the gene
+ * set's whole result into NaN (MetaNeighbor.py:121-130, utils.py:146-147). */
+int mn_mask_dropped(const int32_t* cell_label, const float* inv_norm, const uint8_t* flags, int64_t N,
+                    int32_t* out_label, uint8_t* poison, mn_stream_t stream);
 
 /* Leave-one-study-out combination for the supervised paths (MetaNeighbor.py:198-217
  * and :134-147,170-175).  Input: per-cell sums over joint (study, type) labels,

@@ -27,6 +27,9 @@ SIGNATURES = {
     "mn_rank_normalize_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mn_gene_stats": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "mn_centroids": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "mn_centroids_fixed": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp]),
+    "mn_group_sum_fixed": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "mn_centroids_finish": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "mn_group_sum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "mn_split_f16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "mn_votes_fast": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
@@ -40,6 +43,7 @@ SIGNATURES = {
     "mn_corr_lut": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
     "mn_corr_vote": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "mn_votes_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "mn_mask_dropped": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mn_loso_finalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
     "mn_auroc_workspace_bytes": (_i64, [_i32, _i64, _i32, _i32]),
     "mn_auroc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp]),

@@ -54,6 +54,75 @@ __global__ void centroid_kernel(const __half* __restrict__ d_hi, const __half* _
     if (g + 1 < G) out[(int64_t)l * ldc + g + 1] = (float)a1;
 }
 
+// ---- fixed-point centroids: exact, order-independent sums ----------------------------------------------
+// Every term x*_ig = d_ig / ||d_i|| (|x*| <= 1) is rounded ONCE to a multiple of 2^-38 and the terms are summed
+// as 64-bit integers: the sum does not depend on the order of the cells, on the launch geometry, or on how
+// the cells are dealt to GPUs (partial sums are added with an integer all-reduce), so every world size sees
+// bit-identical centroids.  2^-38 per term is ~1e-11 of a centroid entry, four orders below the float32
+// rounding of the reference's own product; a label may hold up to 2^24 cells before the sum could overflow.
+// grid (ceil(ldc / 2 / T), L, Z): CTA (x, l, z) walks rows r0 + z, r0 + z + Z, ... of label l.
+__global__ void centroid_fixed_kernel(const __half* __restrict__ d_hi, const __half* __restrict__ d_lo, int64_t ldd,
+                                      const double* __restrict__ inv_norm64, const int32_t* __restrict__ row_off,
+                                      int G, unsigned long long* __restrict__ out, int64_t ldc,
+                                      int32_t* __restrict__ n_valid) {
+    const int l = blockIdx.y;
+    const int g2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = 2 * g2;
+    const int Z = gridDim.z;
+    const int r0 = row_off[l] + (int)blockIdx.z, r1 = row_off[l + 1];
+    if (r0 >= r1) return;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        int cnt = 0;
+        for (int r = r0 + (int)threadIdx.x * Z; r < r1; r += 32 * Z) cnt += (inv_norm64[r] > 0.0) ? 1 : 0;
+        cnt = warp_sum(cnt);
+        if (threadIdx.x == 0 && cnt) atomicAdd(n_valid + l, cnt);
+    }
+    if (g >= G) return;
+    long long a0 = 0, a1 = 0;
+    const __half2* ph = reinterpret_cast<const __half2*>(d_hi) + g2;
+    const __half2* pl = d_lo ? reinterpret_cast<const __half2*>(d_lo) + g2 : nullptr;
+    const int64_t stride2 = ldd >> 1;
+#pragma unroll 4
+    for (int r = r0; r < r1; r += Z) {
+        const double w = __ldg(inv_norm64 + r) * MN_CQ_ONE;       // exact: a power-of-two scale
+        float2 v = __half22float2(ph[(int64_t)r * stride2]);
+        if (pl) {
+            const float2 u = __half22float2(pl[(int64_t)r * stride2]);
+            v.x += u.x;   // exact: |d| < 2^15
+            v.y += u.y;
+        }
+        a0 += __double2ll_rn((double)v.x * w);
+        a1 += __double2ll_rn((double)v.y * w);
+    }
+    if (a0) atomicAdd(out + (int64_t)l * ldc + g, (unsigned long long)a0);
+    if (g + 1 < G && a1) atomicAdd(out + (int64_t)l * ldc + g + 1, (unsigned long long)a1);
+}
+
+__global__ void group_sum_fixed_kernel(const long long* __restrict__ in, int64_t ld, int R, int width,
+                                       const int32_t* __restrict__ group, long long* __restrict__ out,
+                                       const int32_t* __restrict__ n_in, int32_t* __restrict__ n_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gq = blockIdx.y;
+    if (c == 0 && n_in) {
+        int t = 0;
+        for (int r = 0; r < R; ++r)
+            if (group[r] == gq) t += n_in[r];
+        n_out[gq] = t;
+    }
+    if (c >= width) return;
+    long long acc = 0;
+    for (int r = 0; r < R; ++r)
+        if (group[r] == gq) acc += in[(int64_t)r * ld + c];
+    out[(int64_t)gq * ld + c] = acc;
+}
+
+__global__ void centroid_finish_kernel(const long long* __restrict__ cq, const int32_t* __restrict__ nq, int64_t n_elem,
+                                       int R, float* __restrict__ C, float* __restrict__ n_valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_elem) C[i] = (float)((double)cq[i] * (1.0 / MN_CQ_ONE));
+    if (i < R) n_valid[i] = (float)nq[i];
+}
+
 __global__ void group_sum_kernel(const float* __restrict__ in, int64_t ld, int R, int width,
                                  const int32_t* __restrict__ group, int n_groups, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,6 +193,17 @@ __global__ void votes_finalize_kernel(const unsigned long long* __restrict__ vot
     }
 }
 
+// test labels of the centroid paths: dropped cells (inv_norm == 0) leave the ranking; *poison is raised when
+// some cell is constant but NON-ZERO (flag bit 0 without bit 1), see include/pymn_b200.h
+__global__ void mask_dropped_kernel(const int32_t* __restrict__ cell_label, const float* __restrict__ inv_norm,
+                                    const uint8_t* __restrict__ flags, int64_t N, int32_t* __restrict__ out_label,
+                                    uint8_t* __restrict__ poison) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    out_label[i] = inv_norm[i] > 0.f ? cell_label[i] : -1;
+    if (poison && flags && (flags[i] & 3) == 1) *poison = 1;
+}
+
 // leave-one-study-out combination (see include/pymn_b200.h)
 __global__ void loso_finalize_kernel(const void* __restrict__ in, int64_t ldi, int is_fixed,
                                      const unsigned long long* __restrict__ degree,
@@ -183,6 +263,48 @@ int mn_centroids(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
     return 0;
 }
 
+int mn_centroids_fixed(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const double* inv_norm64,
+                       const int32_t* row_off, int32_t L, int32_t G, int64_t max_label_rows, int64_t* cq, int64_t ldc,
+                       int32_t* nq, mn_stream_t stream) {
+    MN_CHECK_ARG(d_hi && inv_norm64 && row_off && cq && nq, "mn_centroids_fixed: null pointer");
+    MN_CHECK_ARG(L >= 1 && G >= 1 && ldc >= G && (ldd % 2) == 0, "mn_centroids_fixed: bad shape");
+    const int T = 128;
+    const unsigned gx = (unsigned)((G + 2 * T - 1) / (2 * T));
+    // row slices per label: enough CTAs to fill the machine, at least ~32 rows each
+    int64_t Z = (148 * 16 + (int64_t)gx * L - 1) / ((int64_t)gx * L);
+    const int64_t zmax = max_label_rows > 0 ? (max_label_rows + 31) / 32 : 1;
+    if (Z > zmax) Z = zmax;
+    if (Z > 1024) Z = 1024;
+    if (Z < 1) Z = 1;
+    dim3 grid(gx, (unsigned)L, (unsigned)Z);
+    mn::centroid_fixed_kernel<<<grid, T, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(d_hi), reinterpret_cast<const __half*>(d_lo), ldd, inv_norm64, row_off, G,
+        reinterpret_cast<unsigned long long*>(cq), ldc, nq);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+int mn_group_sum_fixed(const int64_t* in, int64_t ld, int32_t R, int32_t width, const int32_t* group, int32_t n_groups,
+                       int64_t* out, const int32_t* n_in, int32_t* n_out, mn_stream_t stream) {
+    MN_CHECK_ARG(in && group && out && R >= 1 && n_groups >= 1 && width >= 1 && (!n_in || n_out),
+                 "mn_group_sum_fixed: bad arguments");
+    dim3 grid((unsigned)((width + 127) / 128), (unsigned)n_groups);
+    mn::group_sum_fixed_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(in), ld, R, width, group, reinterpret_cast<long long*>(out), n_in, n_out);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+int mn_centroids_finish(const int64_t* cq, const int32_t* nq, int32_t R, int64_t ld, float* centroids, float* n_valid,
+                        mn_stream_t stream) {
+    MN_CHECK_ARG(cq && nq && centroids && n_valid && R >= 1 && ld >= 1, "mn_centroids_finish: bad arguments");
+    const int64_t n = (int64_t)R * ld;
+    mn::centroid_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(cq), nq, n, R, centroids, n_valid);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
 int mn_group_sum(const float* in, int64_t ld, int32_t R, int32_t width, const int32_t* group, int32_t n_groups,
                  float* out, mn_stream_t stream) {
     MN_CHECK_ARG(in && group && out && R >= 1 && n_groups >= 1 && width >= 1, "mn_group_sum: bad arguments");
@@ -207,6 +329,15 @@ int mn_votes_finalize(const uint64_t* votes, const uint64_t* degree, const int32
     mn::votes_finalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const unsigned long long*>(votes), reinterpret_cast<const unsigned long long*>(degree),
         label, N, L, ndn, out, ldo);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+int mn_mask_dropped(const int32_t* cell_label, const float* inv_norm, const uint8_t* flags, int64_t N,
+                    int32_t* out_label, uint8_t* poison, mn_stream_t stream) {
+    MN_CHECK_ARG(cell_label && inv_norm && out_label && N >= 1, "mn_mask_dropped: bad arguments");
+    mn::mask_dropped_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cell_label, inv_norm, flags, N,
+                                                                                          out_label, poison);
     MN_LAUNCH_CHECK();
     return 0;
 }

@@ -22,6 +22,8 @@ constexpr int MN_W_SHIFT = 20;
 constexpr int MN_LUT_DELTA_BITS = 11;
 constexpr uint32_t MN_LUT_DELTA_MAX = (1u << MN_LUT_DELTA_BITS) - 1u;
 constexpr unsigned long long MN_W_ONE = 1ull << MN_W_SHIFT;
+// fixed-point scale of a centroid term (centroids.cu, centroid_fixed_kernel): 2^38
+constexpr double MN_CQ_ONE = 274877906944.0;
 
 // optional CSR view of the expression matrix (scipy.sparse.csr_matrix layout); indptr == nullptr = dense input
 struct CsrIn {

@@ -190,18 +190,42 @@ def gene_stats(X, perm: np.ndarray, seg_off: np.ndarray):
     return med.cpu().numpy(), var.cpu().numpy()
 
 
-def centroids(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: int = 0):
-    """K2.  Returns (C float32 [L + extra_rows, ldd] (extra rows zero), n_valid float32 [L + extra_rows]).
-    The terms are the exact integer ranks times the cells' double-precision scale (cell_limbs)."""
-    C = torch.zeros((L + extra_rows, rc.ldd), dtype=torch.float32, device=rc.d_hi.device)
-    n_valid = torch.zeros((L + extra_rows,), dtype=torch.float32, device=rc.d_hi.device)
-    inv64 = cell_limbs(rc)[3]
-    _lib.call("mn_centroids", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, inv64, row_off, L, rc.G, C, rc.ldd, n_valid)
+def centroids_fixed(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: int = 0, max_label_rows: int = 0):
+    """K2, fixed-point form.  Returns (Cq int64 [L + extra_rows, ldd] = sum over the label's kept cells of
+    x* rounded to multiples of 2^-38, nq int32 [L + extra_rows] kept cells): exact integer sums, so partial
+    results of different GPUs add (all-reduce) to bit-identical centroids for every world size."""
+    dev = rc.d_hi.device
+    Cq = torch.zeros((L + extra_rows, rc.ldd), dtype=torch.int64, device=dev)
+    nq = torch.zeros((L + extra_rows,), dtype=torch.int32, device=dev)
+    if rc.M > 0 and L > 0:
+        inv64 = cell_limbs(rc)[3]
+        _lib.call("mn_centroids_fixed", rc.d_hi, rc.d_lo, rc.ldd, inv64, row_off, L, rc.G,
+                  int(max_label_rows) if max_label_rows else rc.M, Cq, rc.ldd, nq)
+    return Cq, nq
+
+
+def group_sum_fixed_into(Cq, nq, L, group: torch.Tensor, n_groups: int):
+    """Study centroids / study sizes appended as rows L.. of Cq / nq (integer sums of the label rows)."""
+    ld = int(Cq.stride(0))
+    _lib.call("mn_group_sum_fixed", Cq, ld, L, ld, group, n_groups, Cq[L:], nq, nq[L:])
+
+
+def centroids_finish(Cq, nq):
+    """(C float32 [R, ld], n_valid float32 [R]) of fixed-point centroid sums."""
+    R, ld = int(Cq.shape[0]), int(Cq.stride(0))
+    C = torch.empty((R, ld), dtype=torch.float32, device=Cq.device)
+    n_valid = torch.empty((R,), dtype=torch.float32, device=Cq.device)
+    _lib.call("mn_centroids_finish", Cq, nq, R, ld, C, n_valid)
     return C, n_valid
 
 
+def centroids(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: int = 0, max_label_rows: int = 0):
+    """K2.  Returns (C float32 [L + extra_rows, ldd] (extra rows zero), n_valid float32 [L + extra_rows])."""
+    return centroids_finish(*centroids_fixed(rc, row_off, L, extra_rows, max_label_rows))
+
+
 def group_sum_into(C, n_valid, L, group: torch.Tensor, n_groups: int, width: int):
-    """Study centroids / study sizes appended as rows L.. of C / n_valid."""
+    """Study centroids / study sizes appended as rows L.. of C / n_valid (float form: pretrained models)."""
     ld = int(C.stride(0))
     _lib.call("mn_group_sum", C, ld, L, width, group, n_groups, C[L:])
     _lib.call("mn_group_sum", n_valid, 1, L, 1, group, n_groups, n_valid[L:])
@@ -224,27 +248,31 @@ def cell_limbs(rc: RankedCells):
         a1 = torch.empty((rc.M, ldk), dtype=torch.int8, device=dev)
         a0 = torch.empty((rc.M, ldk), dtype=torch.int8, device=dev)
         inv64 = torch.empty((rc.M,), dtype=torch.float64, device=dev)
-        _lib.call("mn_limb_split_cells", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, rc.M, rc.G, a1, a0, ldk, inv64)
+        if rc.M > 0:
+            _lib.call("mn_limb_split_cells", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, rc.M, rc.G, a1, a0, ldk, inv64)
         rc._limbs = (a1, a0, ldk, inv64)
     return rc._limbs
 
 
 def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col_den=None, col_scale=None,
-                as_double=False):
+                as_double=False, ldo: int = 0):
     """K3, exact form (the product path): votes of all cells for the Nn centroid rows of C (float32 [>= Nn, ld])
     through integer limb products on the int8 tensor cores; the epilogue works in double:
     val = x.c + addend;  with ``den`` (double [S, M]) val = val / den[col_den[n]] * col_scale[n] - 1, otherwise
-    val -= col_scale[n].  Returns [Nn, M] column-major, float32 (rounded once) or float64 (``as_double``)."""
+    val -= col_scale[n].  Returns [Nn, max(M, ldo)] column-major, float32 (rounded once) or float64 (``as_double``)."""
     dev = rc.d_hi.device
     a1, a0, ldk, inv64 = cell_limbs(rc)
     rows_pad = (Nn + 127) // 128 * 128
     limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
     inv_scale = torch.empty((Nn,), dtype=torch.float32, device=dev)
     _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale, None)
-    out = torch.empty((Nn, rc.M), dtype=torch.float64 if as_double else torch.float32, device=dev)
-    _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G,
-              None if as_double else out, out if as_double else None, rc.M,
-              den, int(den.stride(0)) if den is not None else 0, col_den, col_scale)
+    ldo = max(int(ldo), rc.M)          # (a pitch > M leaves zeroed padding: equal blocks for the votes exchange)
+    out = (torch.zeros if ldo > rc.M else torch.empty)((Nn, ldo), dtype=torch.float64 if as_double else torch.float32,
+                                                       device=dev)
+    if rc.M > 0:
+        _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G,
+                  None if as_double else out, out if as_double else None, ldo,
+                  den, int(den.stride(0)) if den is not None else 0, col_den, col_scale)
     return out
 
 
@@ -255,8 +283,9 @@ def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int):
     q32 = torch.empty((S, ldk), dtype=torch.int32, device=dev)
     inv_scale = torch.empty((S,), dtype=torch.float32, device=dev)
     _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), S, rc.G, None, ldk, S, inv_scale, q32)
-    out = torch.empty((S, rc.M), dtype=torch.float64, device=dev)
-    _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, q32, inv_scale, addend, S, out, rc.M)
+    out = torch.empty((S, max(rc.M, 1)), dtype=torch.float64, device=dev)
+    if rc.M > 0:
+        _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, q32, inv_scale, addend, S, out, int(out.stride(0)))
     return out
 
 
@@ -269,17 +298,26 @@ def votes_fast(rc: RankedCells, b_hi, b_lo, inv_scale, addend, Nn: int):
 
 
 def auroc(votes: torch.Tensor, ncols: int, denom, col_denom, seg_off: torch.Tensor, n_seg: int,
-          cell_label: torch.Tensor, n_labels: int):
+          cell_label: torch.Tensor, n_labels: int, out: torch.Tensor = None):
     """K6.  votes float32 [>=ncols, M].  Returns (auroc float64 [n_labels, ncols], n_pos int32 [n_labels])."""
     M = int(votes.shape[1])
     dev = votes.device
-    out = torch.empty((n_labels, ncols), dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty((n_labels, ncols), dtype=torch.float64, device=dev)
     n_pos = torch.empty((n_labels,), dtype=torch.int32, device=dev)
     wbytes = _lib.auroc_workspace_bytes(ncols, M, n_seg, n_labels)
     ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
     _lib.call("mn_auroc", votes, int(votes.stride(0)), ncols, denom, col_denom, seg_off, n_seg, cell_label,
               n_labels, M, out, n_pos, ws, wbytes)
     return out, n_pos
+
+
+def mask_dropped(cell_label: torch.Tensor, inv_norm: torch.Tensor, flags=None, poison=None) -> torch.Tensor:
+    """Test labels with the dropped cells (inv_norm == 0) set to -1; ``poison`` (uint8 [1]) is raised when a cell
+    is constant but non-zero (see mn_mask_dropped)."""
+    out = torch.empty_like(cell_label)
+    _lib.call("mn_mask_dropped", cell_label, inv_norm, flags, int(cell_label.numel()), out, poison)
+    return out
 
 
 def one_vs_best(votes, ncols, denom, col_denom, seg_lab_off, n_seg, lab_row_off, cell_label, n_labels, auc):
@@ -293,79 +331,189 @@ def one_vs_best(votes, ncols, denom, col_denom, seg_lab_off, n_seg, lab_row_off,
 # ---------------------------------------------------------------------------
 # pipelines
 # ---------------------------------------------------------------------------
-def _score_against_centroids(rc: RankedCells, lay: LabelLayout, C, n_valid, n_train, train_study, n_train_studies,
-                             ndn: bool, ovb: bool, timer=None):
-    """predict_and_score (MetaNeighborUS.py:310-387) for all test studies at once.
-    C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids.
+REF_BLOCK = 4096        # input cells whose mean vote centres a column (see _column_reference)
 
-    Multi-GPU (torch.distributed initialised, one process per GPU): every train column is an independent
-    unit of the vote GEMM, the AUROC sort and the one-vs-best contest, so the columns are dealt round-robin
-    to the ranks (K1 and the centroid sums are replicated: a few ms) and the L_test x L_train table is
-    assembled with one all-gather of the column slices."""
+
+@dataclass
+class CellShard:
+    """The cells one rank owns in the centroid paths (cells are the data-parallel unit).
+
+    Rank r owns the contiguous block [lo, hi) of INPUT rows (what it uploads through the public API); ``rows``
+    lists them in (study, label)-sorted order -- a subsequence of the global device row order ``lay.perm`` --
+    and ``lab_row_off`` are the label ranges of that local order.  ``gidx[p]`` is where global device row p
+    sits in the concatenation of the ranks' (zero-padded, ``per`` cells each) local orders: a gather through it
+    puts exchanged per-cell arrays into global device row order."""
+    rank: int
+    world: int
+    N: int
+    per: int
+    lo: int
+    hi: int
+    rows: np.ndarray
+    lab_row_off: np.ndarray
+    max_label_rows: int
+    gidx: np.ndarray
+
+
+def cell_shard(lay: LabelLayout, rank: int, world: int) -> CellShard:
+    perm = np.asarray(lay.perm)
+    N, L = int(perm.shape[0]), len(lay.row_labels)
+    if world == 1:
+        counts = np.diff(np.asarray(lay.lab_row_off))
+        return CellShard(0, 1, N, N, 0, N, perm, np.asarray(lay.lab_row_off, np.int32),
+                         int(counts.max()) if L else 0, None)
+    lo, hi, per = shard_rows(N, rank, world)
+    mine = (perm >= lo) & (perm < hi)
+    counts = np.bincount(np.asarray(lay.cell_label)[mine], minlength=L)
+    src = perm // per
+    lpos = np.empty(N, np.int64)
+    for r in range(world):
+        idx = np.flatnonzero(src == r)
+        lpos[idx] = np.arange(idx.shape[0])
+    return CellShard(rank, world, N, per, lo, hi, perm[mine], np.concatenate([[0], np.cumsum(counts)]).astype(np.int32),
+                     int(counts.max()) if L else 0, src.astype(np.int64) * per + lpos)
+
+
+def _gather_cells(local: torch.Tensor, sh: CellShard, gidx: torch.Tensor) -> torch.Tensor:
+    """Per-cell array of the own cells (local order) -> the same for all N cells in global device row order."""
+    if sh.world == 1:
+        return local
+    return gather_rows(local, sh.per, sh.world).index_select(0, gidx)
+
+
+def _all_reduce_sum(*tensors):
+    import torch.distributed as dist
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def _device_matrix(X):
+    """(expression matrix on the device, input row id of its first row) for whatever the caller handed in:
+    a ShardedUpload (the rank holds only its block of input rows), an AsyncUpload, a host / device array or CSR."""
+    if isinstance(X, ShardedUpload):
+        return X.X_local, X.lo
+    if isinstance(X, AsyncUpload):
+        return X.wait_all(), 0
+    return to_device_matrix(X), 0
+
+
+def local_ranked_cells(Xd, base: int, sh: CellShard, drop_mode=0):
+    """K1 over this rank's cells in local label-sorted order (``Xd`` row 0 = input row ``base``)."""
+    return rank_normalize(Xd, row_index=_i32(sh.rows - base), drop_mode=drop_mode)
+
+
+def _column_reference(Xd, base: int, sh: CellShard, C: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """mu[n] = mean over the first min(N, REF_BLOCK) INPUT cells of x* . C[n] (double [n_rows]): the value a
+    column's votes are centred on before their one float32 rounding (any constant is a monotone map of the
+    column, to which K6 / K7 are invariant; a typical vote keeps the rounding at ~1e-9 of the vote where the
+    cells crowd).  The block's cell sum is a fixed-point integer sum (all-reduced), so every world size
+    centres on the same value."""
+    dev = C.device
+    n_ref = min(sh.N, REF_BLOCK)
+    b_lo, b_hi = sh.lo, min(sh.hi, n_ref)
+    ldd = int(C.stride(0))
+    if b_hi > b_lo:
+        rb = rank_normalize(Xd, row_index=torch.arange(b_lo - base, b_hi - base, dtype=torch.int32, device=dev),
+                            drop_mode=0)
+        m = b_hi - b_lo
+        nb = (m + 31) // 32
+        off = torch.clamp(torch.arange(0, nb + 1, dtype=torch.int32, device=dev) * 32, max=m)
+        Sq, nq = centroids_fixed(rb, off, nb, max_label_rows=32)
+        tot = torch.cat([Sq.sum(dim=0), nq.sum().to(torch.int64).reshape(1)])
+    else:
+        tot = torch.zeros((ldd + 1,), dtype=torch.int64, device=dev)
+    if sh.world > 1:
+        _all_reduce_sum(tot)
+    mean_cell = tot[:ldd].double() * (2.0 ** -38) / tot[ldd].clamp(min=1).double()
+    return (C[:n_rows].double() * mean_cell).sum(dim=1)
+
+
+def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: LabelLayout, C, n_valid, n_train, train_study,
+                             n_train_studies, ndn: bool, ovb: bool, timer=None):
+    """predict_and_score (MetaNeighborUS.py:310-387) for all test studies at once.
+    C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids
+    (identical on every rank); ``rc`` = this rank's ranked cells (local order of ``sh``).
+
+    Multi-GPU (one process per GPU): cells are the unit of the vote GEMM -- every rank computes the votes of ITS
+    cells for all train columns -- and train columns are the unit of the AUROC sort and the one-vs-best
+    contest, so one all-to-all turns [all columns, own cells] into [own columns, all cells] (column j lives on
+    rank j % world), and one all-gather assembles the L_test x L_train table.  Votes are exact integer dot
+    products scaled in double, so every world size produces bit-identical tables."""
     dev = rc.d_hi.device
-    rank, world, _ = dist_shard()
+    rank, world = sh.rank, sh.world
     n_lab = len(lay.row_labels)
     n_seg = len(lay.studies)
-    cols = torch.arange(rank, n_train, world, device=dev) if world > 1 else None
-    n_loc = int(cols.numel()) if cols is not None else n_train
-    kept = rc.inv_norm > 0
-    cell_label_all = _i32(lay.cell_label)
-    cell_label = torch.where(kept, cell_label_all, torch.full_like(cell_label_all, -1))
-    seg_off = _i32(lay.seg_off)
-    if cols is not None:
-        rows = torch.cat([cols, torch.arange(n_train, n_train + n_train_studies, device=dev)])
-        C = C.index_select(0, rows).contiguous()
-        n_valid = n_valid.index_select(0, rows).contiguous()
-        train_study = train_study.index_select(0, cols).contiguous()
     t = timer
+    n_max = (n_train + world - 1) // world
+    n_loc = len(range(rank, n_train, world))
+    gidx = to_device(sh.gidx) if world > 1 else None
+    flags = _gather_cells(rc.flags, sh, gidx)
+    cell_label = mask_dropped(_i32(lay.cell_label), _gather_cells(rc.inv_norm, sh, gidx))
+    seg_off = _i32(lay.seg_off)
+    if t: t.start("votes_gemm")
+    # Exact integer dot products; the node-degree ratio is taken in double inside the epilogue and centred on a
+    # per-column reference so that its one float32 rounding resolves ~1e-9 of the ratio where the cells crowd
+    # (rounding numerator and denominator to float32 first costs 3-4 rank flips per AUROC cell at 5,000 cells
+    # per study).
+    n_b = n_train + (n_train_studies if ndn else 0)
+    mu = _column_reference(Xd, base, sh, C, n_b)
+    if world > 1:
+        # columns in destination order: rank d's columns d, d + world, ... as one block of n_max rows (padding
+        # rows repeat column 0 and are dropped after the exchange)
+        order = np.zeros(world * n_max, np.int64)
+        for d in range(world):
+            cols_d = np.arange(d, n_train, world)
+            order[d * n_max:d * n_max + len(cols_d)] = cols_d
+        order = to_device(order)
+    else:
+        order = None
+    pick = (lambda v: v.index_select(0, order).contiguous()) if order is not None else (lambda v: v[:n_train].contiguous())
+    n_cols = world * n_max if world > 1 else n_train
+    ldo = sh.per if world > 1 else 0
+    if ndn:
+        addend = n_valid[:n_b].contiguous()
+        num_ref = mu[:n_train] + addend[:n_train].double()
+        den_ref = (mu[n_train:] + addend[n_train:].double()).index_select(0, train_study.long())
+        ref = num_ref / den_ref
+        scale = torch.where(torch.isfinite(ref) & (ref > 0), 1.0 / ref, torch.ones_like(ref))
+        den64 = votes_den64(rc, C[n_train:n_b], addend[n_train:n_b].contiguous(), n_train_studies)
+        out = votes_exact(rc, pick(C), pick(addend), n_cols, den=den64, col_den=pick(train_study),
+                          col_scale=pick(scale), ldo=ldo)
+    else:
+        out = votes_exact(rc, pick(C), None, n_cols, col_scale=pick(mu), ldo=ldo)
+    if world > 1:
+        out = exchange_votes(out, sh, n_max, gidx)
+    if t: t.stop("votes_gemm")
     if n_loc > 0:
-        n_b = n_loc + (n_train_studies if ndn else 0)
-        if t: t.start("votes_gemm")
-        addend = n_valid[:n_b].contiguous() if ndn else None
-        if _os.environ.get("MN_VOTES_F16"):        # A/B switch: the fp16-plane form (FP32 accumulators)
-            b_hi, b_lo, inv_scale = split_f16(C[:n_b], rc.G)
-            out = votes_fast(rc, b_hi, b_lo, inv_scale, addend, n_b)
-            denom = out[n_loc:] if ndn else None
-            col_denom = train_study if ndn else None
-        else:
-            # Exact integer dot products; the node-degree ratio is taken in double inside the epilogue and centred
-            # on a per-column reference so that its one float32 rounding resolves ~1e-9 of the ratio where the
-            # cells crowd (rounding numerator and denominator to float32 first costs 3-4 rank flips per AUROC
-            # cell at 5,000 cells per study).  Reference = the column's mean vote over a block of cells: any
-            # positive constant is a monotone map of the column, to which K6 / K7 are invariant.
-            m0 = min(rc.M, 4096)               # (as 32-cell pseudo-labels: K2 walks a label's rows serially)
-            nb = max(1, m0 // 32)
-            Cs, ns = centroids(rc, torch.arange(0, 32 * nb + 1, 32, dtype=torch.int32, device=dev)
-                               if m0 >= 32 else torch.tensor([0, m0], dtype=torch.int32, device=dev), nb)
-            mu = ((C[:n_b] * Cs.sum(dim=0)).sum(dim=1) / ns.sum().clamp(min=1.0)).double()
-            if ndn:
-                num_ref = mu[:n_loc] + addend[:n_loc].double()
-                den_ref = (mu[n_loc:] + addend[n_loc:].double()).index_select(0, train_study.long())
-                ref = num_ref / den_ref
-                scale = torch.where(torch.isfinite(ref) & (ref > 0), 1.0 / ref, torch.ones_like(ref)).contiguous()
-                den64 = votes_den64(rc, C[n_loc:n_b], addend[n_loc:n_b].contiguous(), n_train_studies)
-                out = votes_exact(rc, C, addend[:n_loc].contiguous(), n_loc, den=den64, col_den=train_study,
-                                  col_scale=scale)
-            else:
-                out = votes_exact(rc, C, None, n_loc, col_scale=mu[:n_loc].contiguous())
-            denom = col_denom = None
-        if t: t.stop("votes_gemm")
         if t: t.start("auroc")
-        auc, n_pos = auroc(out, n_loc, denom, col_denom, seg_off, n_seg, cell_label, n_lab)
+        auc, n_pos = auroc(out, n_loc, None, None, seg_off, n_seg, cell_label, n_lab)
         if t: t.stop("auroc")
         res = auc
         if ovb:
             if t: t.start("one_vs_best")
-            res = one_vs_best(out, n_loc, denom, col_denom, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
+            res = one_vs_best(out, n_loc, None, None, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
                               cell_label, n_lab, auc)
             if t: t.stop("one_vs_best")
     else:
         auc = res = torch.empty((n_lab, 0), dtype=torch.float64, device=dev)
         n_pos = torch.zeros((n_lab,), dtype=torch.int32, device=dev)
-    if cols is None:
-        return res, auc, n_pos
+    if world == 1:
+        return res, auc, n_pos, flags
     return (_gather_columns(res, n_train, rank, world), _gather_columns(auc, n_train, rank, world),
-            _allreduce_max(n_pos))
+            _allreduce_max(n_pos), flags)
+
+
+def exchange_votes(out: torch.Tensor, sh: CellShard, n_max: int, gidx: torch.Tensor) -> torch.Tensor:
+    """The votes exchange of the cell-sharded centroid path: ``out`` [world * n_max, per] holds the votes of this
+    rank's cells (local order, zero-padded to ``per``) for ALL train columns, destination rank d's columns in rows
+    [d * n_max, (d + 1) * n_max).  One all-to-all hands every rank its own columns for the cells of all ranks;
+    returns [n_max, N] with the cells in global device row order."""
+    import torch.distributed as dist
+    world = sh.world
+    recv = torch.empty_like(out)
+    dist.all_to_all_single(recv.view(-1), out.view(-1))
+    # [source rank, column, local cell] -> [column, global device row]
+    return recv.view(world, n_max, sh.per).permute(1, 0, 2).reshape(n_max, world * sh.per).index_select(1, gidx)
 
 
 def _gather_columns(local: torch.Tensor, n_total: int, rank: int, world: int) -> torch.Tensor:
@@ -390,9 +538,9 @@ def _allreduce_max(t: torch.Tensor) -> torch.Tensor:
 
 
 def ranked_cells(X, lay: LabelLayout, drop_mode=0) -> RankedCells:
-    """K1 over all cells, in label-sorted order, however the matrix arrives: host / device array or CSR
-    (upload, then rank), an AsyncUpload (wait for the chunks), or a ShardedUpload (multi-GPU: rank the own
-    slice, all-gather the planes)."""
+    """K1 over ALL cells, in label-sorted order (the full-network and supervised paths), however the matrix
+    arrives: host / device array or CSR (upload, then rank), an AsyncUpload (wait for the chunks), or a
+    ShardedUpload (multi-GPU: rank the own slice, all-gather the planes)."""
     if isinstance(X, ShardedUpload):
         return ranked_cells_sharded(X, lay, drop_mode)
     Xd = X.wait_all() if isinstance(X, AsyncUpload) else to_device_matrix(X)
@@ -403,21 +551,33 @@ def _host_tables(res, auc, n_pos, flags):
     return dict(table=res.cpu().numpy(), auroc=auc.cpu().numpy(), n_pos=n_pos.cpu().numpy(), flags=flags.cpu().numpy())
 
 
+def _label_centroids(rc: RankedCells, sh: CellShard, L: int, extra_rows: int = 0):
+    """Fixed-point label centroids over the cells of ALL ranks: local partial sums + one integer all-reduce."""
+    Cq, nq = centroids_fixed(rc, _i32(sh.lab_row_off), L, extra_rows, sh.max_label_rows)
+    if sh.world > 1:
+        _all_reduce_sum(Cq, nq)
+    return Cq, nq
+
+
 def us_fast_device(X, lay: LabelLayout, ndn=True, ovb=False, timer=None):
-    """metaNeighborUS_fast with every result left on the device: (table, auroc, n_pos, flags)."""
+    """metaNeighborUS_fast with every result left on the device: (table, auroc, n_pos, flags).
+    With torch.distributed initialised on > 1 ranks the cells are sharded (cell_shard)."""
     t = timer
+    rank, world, _ = dist_shard()
+    sh = cell_shard(lay, rank, world)
     if t: t.start("rank_normalize")
-    rc = ranked_cells(X, lay, 0)
+    Xd, base = _device_matrix(X)
+    rc = local_ranked_cells(Xd, base, sh, 0)
     if t: t.stop("rank_normalize")
     L, S = len(lay.row_labels), len(lay.studies)
     if t: t.start("centroids")
-    C, n_valid = centroids(rc, _i32(lay.lab_row_off), L, extra_rows=S)
+    Cq, nq = _label_centroids(rc, sh, L, extra_rows=S)
     train_study = _i32(lay.label_study)
     if ndn:
-        group_sum_into(C, n_valid, L, train_study, S, rc.G)
+        group_sum_fixed_into(Cq, nq, L, train_study, S)
+    C, n_valid = centroids_finish(Cq, nq)
     if t: t.stop("centroids")
-    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, L, train_study, S, ndn, ovb, timer)
-    return res, auc, n_pos, rc.flags
+    return _score_against_centroids(Xd, base, rc, sh, lay, C, n_valid, L, train_study, S, ndn, ovb, timer)
 
 
 def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
@@ -432,8 +592,11 @@ def us_pretrained_device(X, lay: LabelLayout, model_centroids, model_n, model_st
     """MetaNeighborUS_from_trained with every result left on the device.  The model arrays may be host
     arrays or device tensors: centroids float [L_train, G] (rows = model columns), n [L_train], study int [L_train]."""
     t = timer
+    rank, world, _ = dist_shard()
+    sh = cell_shard(lay, rank, world)
     if t: t.start("rank_normalize")
-    rc = ranked_cells(X, lay, 0)
+    Xd, base = _device_matrix(X)
+    rc = local_ranked_cells(Xd, base, sh, 0)
     if t: t.stop("rank_normalize")
     if t: t.start("centroids")
     Lt = int(model_centroids.shape[0])
@@ -447,8 +610,7 @@ def us_pretrained_device(X, lay: LabelLayout, model_centroids, model_n, model_st
     if ndn:
         group_sum_into(C, n_valid, Lt, train_study, n_model_studies, rc.G)
     if t: t.stop("centroids")
-    res, auc, n_pos = _score_against_centroids(rc, lay, C, n_valid, Lt, train_study, n_model_studies, ndn, ovb, timer)
-    return res, auc, n_pos, rc.flags
+    return _score_against_centroids(Xd, base, rc, sh, lay, C, n_valid, Lt, train_study, n_model_studies, ndn, ovb, timer)
 
 
 def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.ndarray, model_study: np.ndarray,
@@ -459,11 +621,15 @@ def us_pretrained(X, lay: LabelLayout, model_centroids: np.ndarray, model_n: np.
 
 
 def train_model(X, lay: LabelLayout):
-    """trainModel: returns dict(centroids float32 [L, G], n_cells [L], flags [N] device row order)."""
-    rc = ranked_cells(X, lay, 1)
+    """trainModel: returns dict(centroids float32 [L, G], n_cells [L], flags [N] device row order).
+    Multi-GPU: every rank sums its own cells, one integer all-reduce."""
+    rank, world, _ = dist_shard()
+    sh = cell_shard(lay, rank, world)
+    rc = local_ranked_cells(*_device_matrix(X), sh, 1)
     L = len(lay.row_labels)
-    C, n_valid = centroids(rc, _i32(lay.lab_row_off), L)
-    return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=rc.flags.cpu().numpy())
+    C, n_valid = centroids_finish(*_label_centroids(rc, sh, L))
+    flags = _gather_cells(rc.flags, sh, to_device(sh.gidx) if world > 1 else None)
+    return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=flags.cpu().numpy())
 
 
 LAST_SPILL = {}         # what the last rho_spill_buffer call decided (bench.py reports it)
@@ -517,7 +683,7 @@ def release_spill_cache():
 
 
 def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAULT_NBINS, shard=(0, 1),
-                       reduce_fn=None, spill_tiles=None):
+                       reduce_fn=None, spill_tiles=None, spill=None):
     """K4/K5: two tensor-core passes over the (never stored) cell x cell network.
     ``shard`` = (rank, world): this GPU handles every world-th 128-row tile; ``reduce_fn``
     (an in-place sum all-reduce over ranks) is applied to the histogram before the LUT and
@@ -528,16 +694,18 @@ def corr_network_votes(rc: RankedCells, label: torch.Tensor, L: int, nbins=DEFAU
     dev = rc.d_hi.device
     N = rc.M
     rank, world = shard
-    hist = torch.zeros((nbins,), dtype=torch.int64, device=dev)
-    spill, n_sp = rho_spill_buffer(N, rank, world, nbins, dev, reserve_bytes=N * (L + 1) * 8, max_tiles=spill_tiles)
+    zbuf = torch.zeros((nbins + N * L + N,), dtype=torch.int64, device=dev)       # one fill for the three accumulators
+    hist, votes, degree = zbuf[:nbins], zbuf[nbins:nbins + N * L].view(N, L), zbuf[nbins + N * L:]
+    if spill is not None:
+        spill, n_sp = spill
+    else:
+        spill, n_sp = rho_spill_buffer(N, rank, world, nbins, dev, reserve_bytes=N * (L + 1) * 8, max_tiles=spill_tiles)
     _lib.call("mn_corr_hist", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, hist,
               spill, n_sp)
     if reduce_fn is not None:
         reduce_fn(hist)
     lut = torch.empty((nbins + 2,), dtype=torch.int32, device=dev)
     _lib.call("mn_corr_lut", hist, nbins, N, lut)
-    votes = torch.zeros((N, L), dtype=torch.int64, device=dev)
-    degree = torch.zeros((N,), dtype=torch.int64, device=dev)
     _lib.call("mn_corr_vote", rc.d_hi, rc.d_lo, rc.ldd, rc.inv_norm, N, 0, N, rank, world, rc.G, nbins, lut,
               label, L, votes, degree, spill, n_sp)
     if reduce_fn is not None:
@@ -851,26 +1019,30 @@ class SupervisedContext:
     lab_row_off: torch.Tensor
     seg_off: torch.Tensor
     n_studies: int
+    max_label_rows: int = 0
 
 
 def supervised_prepare(X, lay: LabelLayout) -> SupervisedContext:
     """Upload the shared expression matrix and the label layout once (MetaNeighbor.py:80-83)."""
+    counts = np.diff(np.asarray(lay.lab_row_off))
     return SupervisedContext(to_device(X, torch.float32), _i32(lay.perm), _i32(lay.cell_label), _i32(lay.cell_study),
-                             _i32(lay.lab_row_off), _i32(lay.seg_off), len(lay.studies))
+                             _i32(lay.lab_row_off), _i32(lay.seg_off), len(lay.studies),
+                             int(counts.max()) if len(counts) else 0)
 
 
 def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types: int, ndn=True, fast=False,
-                       nbins=DEFAULT_NBINS, poison_out: torch.Tensor = None):
+                       nbins=DEFAULT_NBINS, poison_out: torch.Tensor = None, out: torch.Tensor = None, spill=None):
     """One gene set.  ``col_index``: int32 device tensor of the set's gene columns.  The layout behind ``ctx``
     is that of JOINT labels study*K + type (all S*K ids, empty ranges allowed).  Returns the float64
-    [S*K, K] AUROC table (rows = joint test labels) ON THE DEVICE: nothing here synchronises, so the
-    caller can keep enqueuing gene sets and fetch all tables with one copy.
+    [S*K, K] AUROC table (rows = joint test labels) ON THE DEVICE (written into ``out`` when given): nothing here
+    synchronises, so the caller can keep enqueuing gene sets and fetch all tables with one copy.
 
-    ``poison_out`` (0-dim bool tensor, fast path): set when some cell is constant and NON-ZERO over the gene
+    ``poison_out`` (uint8 [1] tensor, fast path): set when some cell is constant and NON-ZERO over the gene
     set.  score_low_mem only drops cells whose sum is <= 0 (MetaNeighbor.py:121), so such a cell normalises
     to a NaN row (utils.py:146-147) that poisons `voters @ voter_id` and the candidates' ranks: the
     reference's result for the gene set is NaN for every cell type.  K1 drops the cell
-    (flag bit 0 without bit 1); the caller reproduces the NaN column from this flag."""
+    (flag bit 0 without bit 1); the caller reproduces the NaN column from this flag.
+    ``spill``: (buffer, tiles) of the rho spill decided once per run (None = decide here)."""
     S = ctx.n_studies
     K = n_types
     Xd = ctx.Xd
@@ -879,18 +1051,15 @@ def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types:
     cell_label, cell_study = ctx.cell_label, ctx.cell_study
     vmat = torch.empty((K, rc.M), dtype=torch.float32, device=dev)
     if fast:
-        C, n_valid = centroids(rc, ctx.lab_row_off, S * K)
-        out = votes_exact(rc, C, None, S * K)
-        _lib.call("mn_loso_finalize", out, rc.M, 0, None, n_valid, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
-        kept = rc.inv_norm > 0
-        test_label = torch.where(kept, cell_label, torch.full_like(cell_label, -1))
-        if poison_out is not None:
-            poison_out.copy_(((rc.flags & 3) == 1).any())
+        C, n_valid = centroids(rc, ctx.lab_row_off, S * K, max_label_rows=ctx.max_label_rows)
+        votes = votes_exact(rc, C, None, S * K)
+        _lib.call("mn_loso_finalize", votes, rc.M, 0, None, n_valid, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
+        test_label = mask_dropped(cell_label, rc.inv_norm, rc.flags, poison_out)
     else:
-        votes, degree, _, _ = corr_network_votes(rc, cell_label, S * K, nbins)
+        votes, degree, _, _ = corr_network_votes(rc, cell_label, S * K, nbins, spill=spill)
         _lib.call("mn_loso_finalize", votes, S * K, 1, degree, None, cell_study, rc.M, S, K, int(bool(ndn)), vmat, rc.M)
         test_label = cell_label
-    auc, _ = auroc(vmat, K, None, None, ctx.seg_off, S, test_label, S * K)
+    auc, _ = auroc(vmat, K, None, None, ctx.seg_off, S, test_label, S * K, out=out)
     return auc
 
 
@@ -898,14 +1067,19 @@ def supervised_tables(ctx: SupervisedContext, all_cols: torch.Tensor, offs, n_ty
                       nbins=DEFAULT_NBINS):
     """All gene sets of one rank, back to back on the current stream (MetaNeighbor.py:84-93).  ``all_cols``:
     int32 device tensor, the gene columns of set j are all_cols[offs[j]:offs[j + 1]].  Returns
-    (tables float64 [n_sets, S*K, K] on the device, poison bool [n_sets] -- see supervised_geneset);
-    nothing synchronises."""
+    (tables float64 [n_sets, S*K, K] on the device, poison uint8 [n_sets] -- see supervised_geneset);
+    nothing synchronises.  The rho spill of the full-network mode is sized once for the whole run (its size
+    depends on N only; asking the driver for the free memory costs more than a gene set's kernels)."""
     n_sets = len(offs) - 1
     dev = ctx.Xd.device
     S, K = ctx.n_studies, n_types
+    N = int(ctx.perm.numel())
     tables = torch.empty((n_sets, S * K, K), dtype=torch.float64, device=dev)
-    poison = torch.zeros((max(1, n_sets),), dtype=torch.bool, device=dev)
+    poison = torch.zeros((max(1, n_sets),), dtype=torch.uint8, device=dev)
+    spill = None
+    if not fast and n_sets > 0:
+        spill = rho_spill_buffer(N, 0, 1, nbins, dev, reserve_bytes=N * (S * K + 1) * 8 + N * K * 4 + (2 << 30))
     for j in range(n_sets):
-        tables[j] = supervised_geneset(ctx, all_cols[int(offs[j]):int(offs[j + 1])], K, ndn, fast, nbins,
-                                       poison_out=poison[j] if fast else None)
+        supervised_geneset(ctx, all_cols[int(offs[j]):int(offs[j + 1])], K, ndn, fast, nbins,
+                           poison_out=poison[j:j + 1] if fast else None, out=tables[j], spill=spill)
     return tables, poison

@@ -53,7 +53,28 @@ def main():
             engine.dist_shard = saved_shard
         assert np.array_equal(f_multi.values, f_single.values, equal_nan=True), f"fast API table differs (ovb={ovb})"
 
-    # centroid (fast) path: train columns are dealt to the ranks, tables all-gathered
+    # pretrained model: trainModel (cells sharded, integer all-reduce of the centroid sums), then scoring against it
+    import warnings
+
+    def _single(fn):
+        engine.dist_shard = lambda: (0, 1, None)
+        try:
+            return fn()
+        finally:
+            engine.dist_shard = saved_shard
+
+    m_multi = pymn_b200.trainModel(make_adata(inp0), "study_id", "cell_type")
+    m_single = _single(lambda: pymn_b200.trainModel(make_adata(inp0), "study_id", "cell_type"))
+    assert list(m_multi.columns) == list(m_single.columns)
+    assert np.array_equal(m_multi.values, m_single.values, equal_nan=True), "sharded trainModel differs"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        kwp = dict(trained_model=m_multi, symmetric_output=False, save_uns=False)
+        p_multi = pymn_b200.MetaNeighborUS(make_adata(inp0), "study_id", "cell_type", **kwp)
+        p_single = _single(lambda: pymn_b200.MetaNeighborUS(make_adata(inp0), "study_id", "cell_type", **kwp))
+    assert np.array_equal(p_multi.values, p_single.values, equal_nan=True), "sharded pretrained table differs"
+
+    # centroid (fast) path on a device-resident / host matrix: cells sharded, votes exchanged, columns all-gathered
     for ovb in (False, True):
         sharded = engine.us_fast(x, lay, True, ovb)
         saved_shard = engine.dist_shard
@@ -78,7 +99,8 @@ def main():
     assert np.array_equal(tab.values, ref.values, equal_nan=True), "gene-set sharded table differs"
     dist.barrier()
     if rank == 0:
-        print(f"dist check ok on {dist.get_world_size()} GPUs: full-network and supervised tables bit-identical")
+        print(f"dist check ok on {dist.get_world_size()} GPUs: full-network, centroid, pretrained, trainModel and "
+              "supervised tables bit-identical")
     dist.destroy_process_group()
 
 

@@ -80,3 +80,52 @@ def test_sharded_ingestion_row_gather_gloo(tmp_path, n):
         got = np.load(tmp_path / f"rows_{rank}.npy")
         assert got.shape[0] >= n and np.array_equal(got[:n], want) and not got[n:].any()
         assert np.array_equal(np.load(tmp_path / f"vec_{rank}.npy")[:n], want[:, 0])
+
+
+def _worker_cells(rank, world, port, seed, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pymn_b200 import engine
+        from pymn_b200.utils import label_layout
+        rng = np.random.default_rng(seed)
+        n = 37
+        study = rng.choice(np.array(["s1", "s2", "s10"], dtype=object), size=n)
+        ctype = rng.choice(np.array(["a", "b", "c", "d"], dtype=object), size=n)
+        lay = label_layout(study, ctype)
+        sh = engine.cell_shard(lay, rank, world)
+        L = len(lay.row_labels)
+        # the own cells, in local order, are a subsequence of the global device row order with the right label ranges
+        assert np.all((sh.rows >= sh.lo) & (sh.rows < sh.hi)) and len(sh.rows) == sh.hi - sh.lo
+        lab_of_input = np.empty(n, np.int64)
+        lab_of_input[lay.perm] = lay.cell_label
+        for l in range(L):
+            assert np.all(lab_of_input[sh.rows[sh.lab_row_off[l]:sh.lab_row_off[l + 1]]] == l)
+        # per-cell arrays: gather -> global device row order
+        gidx = torch.from_numpy(sh.gidx)
+        got = engine._gather_cells(torch.from_numpy(sh.rows.astype(np.float32)), sh, gidx)
+        assert np.array_equal(got.numpy(), lay.perm.astype(np.float32))
+        # votes exchange: value encodes (column, input row)
+        n_train = 5
+        n_max = (n_train + world - 1) // world
+        out = torch.zeros((world * n_max, sh.per), dtype=torch.float32)
+        for d in range(world):
+            for k, col in enumerate(range(d, n_train, world)):
+                out[d * n_max + k, :len(sh.rows)] = torch.from_numpy(1000.0 * col + sh.rows.astype(np.float32))
+        mine = engine.exchange_votes(out, sh, n_max, gidx)
+        for k, col in enumerate(range(rank, n_train, world)):
+            assert np.array_equal(mine[k].numpy(), 1000.0 * col + lay.perm.astype(np.float32)), (rank, col)
+        np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.ones(1))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_cell_shard_and_votes_exchange_gloo(tmp_path, seed):
+    """Cell-sharded centroid path: each rank owns a block of input rows, sorted locally by label; the
+    all-to-all hands every rank its train columns for all cells in global device row order."""
+    world = 2
+    mp.spawn(_worker_cells, args=(world, _free_port(), seed, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        assert (tmp_path / f"ok_{rank}.npy").exists()
