@@ -249,8 +249,11 @@ class Ctx:
         self.barrier()
         t0 = time.perf_counter()
         out = None
+        self.last_wall_ms = []
         for _ in range(steps):
+            t1 = time.perf_counter()
             out = fn()
+            self.last_wall_ms.append(round((time.perf_counter() - t1) * 1e3, 2))
         self.barrier()
         return self.max_over_ranks((time.perf_counter() - t0) / steps), out
 
@@ -502,6 +505,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     adata_pin = _adata(Xh.numpy(), s_lab, c_lab, G)
     e2e_s, tab = ctx.wall(lambda: api_call(adata_pin), max(1, min(args.warmup, 2)), e2e_steps)
+    e2e_calls_ms = list(ctx.last_wall_ms)
     assert np.array_equal(tab.values, ref_tab), "API table differs from the device-resident run"
     # (N > 1: every rank uploads its own 1/N slice of the matrix -- the total over ranks is the matrix once --
     #  plus the small label arrays on every rank)
@@ -584,7 +588,8 @@ def run_ours(args):
                        "parallelism": f"row-tile sharding x{world}" if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "input": "pinned host array, warm process"},
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "calls_ms": e2e_calls_ms,
+                    "input": "pinned host array, warm process"},
             "e2e_pageable": {"value": pairs / page_s, "unit": UNIT, "ms_per_step": page_s * 1e3,
                              "input": "pageable NumPy array, warm process"},
             "e2e_cold": {"value": pairs / cold_s, "unit": UNIT, "ms": cold_s * 1e3,

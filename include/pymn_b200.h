@@ -76,6 +76,18 @@ int mn_rank_normalize_csr(const int64_t* indptr, const int32_t* indices, const f
                           int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm, int32_t* rank2,
                           int32_t drop_mode, mn_stream_t stream);
 
+/* K1 straight into the operand format of the centroid paths: int8 limb planes a1, a0 [M, ldk] (d = 128 a1 + a0,
+ * a0 in [-64, 63]; G <= 127: a1 = d, a0 = 0; ldk a multiple of 128, padding zero) and the cell's scale in double,
+ * inv_norm64[m] = 1 / ||d_m|| (0 = dropped cell) -- exactly what mn_limb_split_cells derives from the fp16 planes,
+ * without writing the planes or running the split pass.  inv_norm / flags as in mn_rank_normalize. */
+int mn_rank_normalize_limbs(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index,
+                            int64_t M, int32_t G, int8_t* a1, int8_t* a0, int64_t ldk, double* inv_norm64,
+                            float* inv_norm, uint8_t* flags, int32_t drop_mode, mn_stream_t stream);
+int mn_rank_normalize_csr_limbs(const int64_t* indptr, const int32_t* indices, const float* data,
+                                const int32_t* row_index, int64_t M, int32_t G, int8_t* a1, int8_t* a0, int64_t ldk,
+                                double* inv_norm64, float* inv_norm, uint8_t* flags, int32_t drop_mode,
+                                mn_stream_t stream);
+
 /* ---- gene statistics for variableGenes (the step before the hot path) -------------
  * Replaces bottleneck.median(adata.X, axis=0) and np.var(adata.X, axis=0) over the cells of each
  * study (variableGenes.py:22-27, called per study at :69-72).
@@ -112,6 +124,10 @@ int mn_centroids(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
 int mn_centroids_fixed(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, const double* inv_norm64,
                        const int32_t* row_off, int32_t L, int32_t G, int64_t max_label_rows, int64_t* cq, int64_t ldc,
                        int32_t* nq, mn_stream_t stream);
+/* the same from the int8 limb planes of mn_rank_normalize_limbs / mn_limb_split_cells (d = 128 a1 + a0) */
+int mn_centroids_fixed_i8(const int8_t* a1, const int8_t* a0, int64_t ldk, const double* inv_norm64,
+                          const int32_t* row_off, int32_t L, int32_t G, int64_t max_label_rows, int64_t* cq, int64_t ldc,
+                          int32_t* nq, mn_stream_t stream);
 int mn_group_sum_fixed(const int64_t* in, int64_t ld, int32_t R, int32_t width, const int32_t* group, int32_t n_groups,
                        int64_t* out, const int32_t* n_in, int32_t* n_out, mn_stream_t stream);
 int mn_centroids_finish(const int64_t* cq, const int32_t* nq, int32_t R, int64_t ld, float* centroids, float* n_valid,

@@ -25,9 +25,12 @@ SIGNATURES = {
     "mn_launch_count": (_i64, []),
     "mn_rank_normalize": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mn_rank_normalize_csr": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "mn_rank_normalize_limbs": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "mn_rank_normalize_csr_limbs": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mn_gene_stats": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "mn_centroids": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "mn_centroids_fixed": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp]),
+    "mn_centroids_fixed_i8": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp]),
     "mn_group_sum_fixed": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "mn_centroids_finish": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "mn_group_sum": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),

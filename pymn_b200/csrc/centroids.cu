@@ -98,6 +98,43 @@ __global__ void centroid_fixed_kernel(const __half* __restrict__ d_hi, const __h
     if (g + 1 < G && a1) atomicAdd(out + (int64_t)l * ldc + g + 1, (unsigned long long)a1);
 }
 
+// the same sums from the int8 limb planes (d = 128 a1 + a0; G <= 127: d = a1): four genes per thread
+__global__ void centroid_fixed_i8_kernel(const int8_t* __restrict__ a1, const int8_t* __restrict__ a0, int64_t ldk,
+                                         const double* __restrict__ inv_norm64, const int32_t* __restrict__ row_off,
+                                         int G, unsigned long long* __restrict__ out, int64_t ldc,
+                                         int32_t* __restrict__ n_valid) {
+    const int l = blockIdx.y;
+    const int g4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = 4 * g4;
+    const int Z = gridDim.z;
+    const int r0 = row_off[l] + (int)blockIdx.z, r1 = row_off[l + 1];
+    if (r0 >= r1) return;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        int cnt = 0;
+        for (int r = r0 + (int)threadIdx.x * Z; r < r1; r += 32 * Z) cnt += (inv_norm64[r] > 0.0) ? 1 : 0;
+        cnt = warp_sum(cnt);
+        if (threadIdx.x == 0 && cnt) atomicAdd(n_valid + l, cnt);
+    }
+    if (g >= G) return;
+    long long acc[4] = {0, 0, 0, 0};
+    const int hs = G <= 127 ? 1 : 128;          // one digit per rank up to 127 genes: a1 = d, a0 = 0
+    const char4* p1 = reinterpret_cast<const char4*>(a1) + g4;
+    const char4* p0 = reinterpret_cast<const char4*>(a0) + g4;
+    const int64_t stride4 = ldk >> 2;
+#pragma unroll 4
+    for (int r = r0; r < r1; r += Z) {
+        const double w = __ldg(inv_norm64 + r) * MN_CQ_ONE;       // exact: a power-of-two scale
+        const char4 h = p1[(int64_t)r * stride4], q = p0[(int64_t)r * stride4];
+        acc[0] += __double2ll_rn((double)(hs * (int)h.x + (int)q.x) * w);
+        acc[1] += __double2ll_rn((double)(hs * (int)h.y + (int)q.y) * w);
+        acc[2] += __double2ll_rn((double)(hs * (int)h.z + (int)q.z) * w);
+        acc[3] += __double2ll_rn((double)(hs * (int)h.w + (int)q.w) * w);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (g + u < G && acc[u]) atomicAdd(out + (int64_t)l * ldc + g + u, (unsigned long long)acc[u]);
+}
+
 __global__ void group_sum_fixed_kernel(const long long* __restrict__ in, int64_t ld, int R, int width,
                                        const int32_t* __restrict__ group, long long* __restrict__ out,
                                        const int32_t* __restrict__ n_in, int32_t* __restrict__ n_out) {
@@ -280,6 +317,25 @@ int mn_centroids_fixed(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd
     mn::centroid_fixed_kernel<<<grid, T, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __half*>(d_hi), reinterpret_cast<const __half*>(d_lo), ldd, inv_norm64, row_off, G,
         reinterpret_cast<unsigned long long*>(cq), ldc, nq);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
+
+int mn_centroids_fixed_i8(const int8_t* a1, const int8_t* a0, int64_t ldk, const double* inv_norm64,
+                          const int32_t* row_off, int32_t L, int32_t G, int64_t max_label_rows, int64_t* cq, int64_t ldc,
+                          int32_t* nq, mn_stream_t stream) {
+    MN_CHECK_ARG(a1 && a0 && inv_norm64 && row_off && cq && nq, "mn_centroids_fixed_i8: null pointer");
+    MN_CHECK_ARG(L >= 1 && G >= 1 && ldc >= G && ldk >= G && (ldk % 4) == 0, "mn_centroids_fixed_i8: bad shape");
+    const int T = 128;
+    const unsigned gx = (unsigned)((G + 4 * T - 1) / (4 * T));
+    int64_t Z = (148 * 16 + (int64_t)gx * L - 1) / ((int64_t)gx * L);
+    const int64_t zmax = max_label_rows > 0 ? (max_label_rows + 31) / 32 : 1;
+    if (Z > zmax) Z = zmax;
+    if (Z > 1024) Z = 1024;
+    if (Z < 1) Z = 1;
+    dim3 grid(gx, (unsigned)L, (unsigned)Z);
+    mn::centroid_fixed_i8_kernel<<<grid, T, 0, (cudaStream_t)stream>>>(a1, a0, ldk, inv_norm64, row_off, G,
+                                                                      reinterpret_cast<unsigned long long*>(cq), ldc, nq);
     MN_LAUNCH_CHECK();
     return 0;
 }

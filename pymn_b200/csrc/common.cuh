@@ -32,13 +32,24 @@ struct CsrIn {
     const float* data;        // [nnz]
 };
 
+// optional int8 limb output of K1 (the centroid paths' operand format, see limbs.cu): d = 128 a1 + a0 with
+// a0 in [-64, 63] (G <= 127: a1 = d, a0 = 0), row pitch ldk (multiple of 128, padding zero), and the cell's scale
+// 1 / ||d|| in double (0 = dropped cell).  a1 == nullptr: not wanted.
+struct LimbOut {
+    int8_t* a1;
+    int8_t* a0;
+    int64_t ldk;
+    double* inv64;
+};
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
 // rank_warp.cu
 int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                      __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr);
+                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr,
+                     LimbOut limb);
 // auroc_count.cu
 int64_t auroc_count_workspace_bytes(int ncols, int64_t M, int n_seg, int n_labels);
 int launch_auroc_count(const float* votes, int64_t ldv, int ncols, const float* denom, const int32_t* col_denom,
@@ -47,7 +58,7 @@ int launch_auroc_count(const float* votes, int64_t ldv, int ncols, const float* 
 // rank_count.cu
 int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                       __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                      int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr);
+                      int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr, LimbOut limb);
 
 #define MN_CHECK_ARG(cond, ...)              \
     do {                                     \
@@ -87,6 +98,19 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// four centred ranks -> one word of each limb plane (byte u = gene g0 + u)
+__device__ __forceinline__ void limb_pack4(const int d[4], bool one_limb, uint32_t& w1, uint32_t& w0) {
+    w1 = 0u;
+    w0 = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int hi = one_limb ? d[u] : (d[u] + 64) >> 7;      // floor((d + 64) / 128)
+        const int lo = one_limb ? 0 : d[u] - (hi << 7);         // [-64, 63]
+        w1 |= ((uint32_t)hi & 0xffu) << (8 * u);
+        w0 |= ((uint32_t)lo & 0xffu) << (8 * u);
+    }
 }
 
 template <typename T>

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32)
 rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ row_index,
                   const int32_t* __restrict__ col_index, int64_t M, int G, int g_pad, __half* __restrict__ d_hi,
                   __half* __restrict__ d_lo, int64_t ldd, float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
-                  float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode, CsrIn csr) {
+                  float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode, CsrIn csr, LimbOut limb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // 16-bit bins (counts <= G and 2*rank <= 2G + 1 fit for G < 32,768; the launcher checks): two per word,
@@ -191,9 +191,31 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
             inv_norm[row] = drop ? 0.f : (float)inv_true;
             flags[row] = (uint8_t)((zv ? 1 : 0) | (nonpos ? 2 : 0) | (drop ? 4 : 0));
         }
+        if (limb.a1) {
+            // int8 limb planes (the centroid paths): four genes per lane and step, one 32-bit store per plane
+            uint32_t* p1 = reinterpret_cast<uint32_t*>(limb.a1 + row * limb.ldk);
+            uint32_t* p0 = reinterpret_cast<uint32_t*>(limb.a0 + row * limb.ldk);
+            const bool one_limb = G <= 127;
+            for (int g4 = lane; g4 < (int)(limb.ldk >> 2); g4 += 32) {
+                const int g = 4 * g4;
+                int d[4] = {0, 0, 0, 0};
+                if (!drop && g < G) {
+                    const uint2 pr = *reinterpret_cast<const uint2*>(vals + g);       // g_pad is a multiple of 8
+                    const int v[4] = {(int)(pr.x & 0xffffu), (int)(pr.x >> 16), (int)(pr.y & 0xffffu), (int)(pr.y >> 16)};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (g + u < G) d[u] = (int)(v[u] ? tab[v[u]] : zero_r2) - c;
+                }
+                uint32_t w1, w0;
+                limb_pack4(d, one_limb, w1, w0);
+                p1[g4] = w1;
+                p0[g4] = w0;
+            }
+            if (lane == 0) limb.inv64[row] = drop ? 0.0 : inv_true;
+        }
         __half2* ph = reinterpret_cast<__half2*>(d_hi + row * ldd);
         __half2* pl = d_lo ? reinterpret_cast<__half2*>(d_lo + row * ldd) : nullptr;
-        for (int g2 = lane; g2 < (int)(ldd >> 1); g2 += 32) {
+        for (int g2 = lane; d_hi && g2 < (int)(ldd >> 1); g2 += 32) {
             const int g = 2 * g2;
             int d0 = 0, d1 = 0;
             if (!drop && g < G) {
@@ -229,7 +251,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
 
 int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                       __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                      int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr) {
+                      int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr, LimbOut limb) {
     const int g_pad = (G + 7) & ~7;
     if (G >= 32768) {
         set_error("rank_count: G=%d exceeds the 16-bit rank table (max 32767)", G);
@@ -247,7 +269,7 @@ int launch_rank_count(const float* X, int64_t ldx, const int32_t* row_index, con
     const int64_t max_blocks = (int64_t)sms * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     rank_count_kernel<<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(X, ldx, row_index, col_index, M, G, g_pad, d_hi, d_lo,
-                                                                   ldd, inv_norm, flags, xnorm, rank2, drop_mode, csr);
+                                                                   ldd, inv_norm, flags, xnorm, rank2, drop_mode, csr, limb);
     MN_LAUNCH_CHECK();
     return 0;
 }

@@ -42,7 +42,7 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
                                       __half* __restrict__ d_hi, __half* __restrict__ d_lo, int64_t ldd,
                                       float* __restrict__ inv_norm, uint8_t* __restrict__ flags,
                                       float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode,
-                                      int only_overflow, CsrIn csr) {
+                                      int only_overflow, CsrIn csr, LimbOut limb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* skey = reinterpret_cast<uint64_t*>(smem_raw);   // [Pmax]
     int* r2 = reinterpret_cast<int*>(skey + Pmax);            // [G]
@@ -152,9 +152,24 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
             inv_norm[row] = drop ? 0.f : (float)inv_true;
             flags[row] = (uint8_t)((zerovar ? 1 : 0) | (nonpos ? 2 : 0) | (drop ? 4 : 0));
         }
+        if (limb.a1) {
+            uint32_t* p1 = reinterpret_cast<uint32_t*>(limb.a1 + row * limb.ldk);
+            uint32_t* p0 = reinterpret_cast<uint32_t*>(limb.a0 + row * limb.ldk);
+            const bool one_limb = G <= 127;
+            for (int g4 = tid; g4 < (int)(limb.ldk >> 2); g4 += T) {
+                int d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d[u] = (!drop && 4 * g4 + u < G) ? r2[4 * g4 + u] - c : 0;
+                uint32_t w1, w0;
+                limb_pack4(d, one_limb, w1, w0);
+                p1[g4] = w1;
+                p0[g4] = w0;
+            }
+            if (tid == 0) limb.inv64[row] = drop ? 0.0 : inv_true;
+        }
         __half2* ph = reinterpret_cast<__half2*>(d_hi + row * ldd);
         __half2* pl = d_lo ? reinterpret_cast<__half2*>(d_lo + row * ldd) : nullptr;
-        for (int g2 = tid; g2 < (int)(ldd >> 1); g2 += T) {
+        for (int g2 = tid; d_hi && g2 < (int)(ldd >> 1); g2 += T) {
             const int g = 2 * g2;
             const int d0 = (!drop && g < G) ? r2[g] - c : 0;
             const int d1 = (!drop && g + 1 < G) ? r2[g + 1] - c : 0;
@@ -181,11 +196,17 @@ __global__ void rank_normalize_kernel(const float* __restrict__ X, int64_t ldx,
 
 static int rank_dispatch(const float* X, int64_t ldx, mn::CsrIn csr, const int32_t* row_index, const int32_t* col_index,
                          int64_t M, int32_t G, mn_half_t* d_hi, mn_half_t* d_lo, int64_t ldd, float* inv_norm,
-                         uint8_t* flags, float* xnorm, int32_t* rank2, int32_t drop_mode, mn_stream_t stream) {
-    MN_CHECK_ARG((X || csr.indptr) && d_hi && inv_norm && flags, "mn_rank_normalize: null pointer");
+                         uint8_t* flags, float* xnorm, int32_t* rank2, int32_t drop_mode, mn_stream_t stream,
+                         mn::LimbOut limb = mn::LimbOut{nullptr, nullptr, 0, nullptr}) {
+    MN_CHECK_ARG((X || csr.indptr) && (d_hi || limb.a1) && inv_norm && flags, "mn_rank_normalize: null pointer");
     MN_CHECK_ARG(G >= 1 && G <= 16384, "mn_rank_normalize: G=%d outside [1, 16384]", G);
-    MN_CHECK_ARG(ldd >= G && (ldd % 8) == 0, "mn_rank_normalize: ldd=%lld must be >= G and a multiple of 8", (long long)ldd);
-    MN_CHECK_ARG(G <= 2048 || d_lo, "mn_rank_normalize: G=%d > 2048 needs the d_lo plane", G);
+    if (d_hi) {
+        MN_CHECK_ARG(ldd >= G && (ldd % 8) == 0, "mn_rank_normalize: ldd=%lld must be >= G and a multiple of 8", (long long)ldd);
+        MN_CHECK_ARG(G <= 2048 || d_lo, "mn_rank_normalize: G=%d > 2048 needs the d_lo plane", G);
+    }
+    if (limb.a1)
+        MN_CHECK_ARG(limb.a0 && limb.inv64 && limb.ldk >= G && (limb.ldk % 128) == 0,
+                     "mn_rank_normalize_limbs: a0 / inv_norm64 missing or ldk=%lld not a multiple of 128 >= G", (long long)limb.ldk);
     if (M <= 0) return 0;
     // fast path: one warp per cell, register bitonic sort (rank_warp.cu); rows with more than 2048
     // non-zeros (only possible for G > 2048) are flagged and redone below by the CTA-per-cell kernel
@@ -201,13 +222,13 @@ static int rank_dispatch(const float* X, int64_t ldx, mn::CsrIn csr, const int32
         int only_mask = 0;
         if (!getenv("MN_RANK_NOCOUNT")) {
             const int rc = mn::launch_rank_count(X, ldx, row_index, col_index, M, G, hi, lo, ldd, inv_norm, flags, xnorm,
-                                                 rank2, drop_mode, st, csr);
+                                                 rank2, drop_mode, st, csr, limb);
             if (rc) return rc;
             only_mask = 16;
         }
         bool may_overflow = false;
         const int rc = mn::launch_rank_warp(X, ldx, row_index, col_index, M, G, hi, lo, ldd, inv_norm, flags, xnorm, rank2,
-                                            drop_mode, st, &may_overflow, only_mask, csr);
+                                            drop_mode, st, &may_overflow, only_mask, csr, limb);
         if (rc) return rc;
         if (!may_overflow) return 0;
         only_overflow = 1;
@@ -223,7 +244,7 @@ static int rank_dispatch(const float* X, int64_t ldx, mn::CsrIn csr, const int32
     if (only_overflow && grid > 1184) grid = 1184;      // a small persistent grid scans the flags for the few dense rows
     mn::rank_normalize_kernel<<<(unsigned)grid, T, smem, (cudaStream_t)stream>>>(
         X, ldx, row_index, col_index, M, G, Pmax, reinterpret_cast<__half*>(d_hi), reinterpret_cast<__half*>(d_lo),
-        ldd, inv_norm, flags, xnorm, rank2, drop_mode, only_overflow, csr);
+        ldd, inv_norm, flags, xnorm, rank2, drop_mode, only_overflow, csr, limb);
     MN_LAUNCH_CHECK();
     return 0;
 }
@@ -246,4 +267,25 @@ extern "C" int mn_rank_normalize_csr(const int64_t* indptr, const int32_t* indic
     mn::CsrIn csr = {indptr, indices, data};
     return rank_dispatch(nullptr, 0, csr, row_index, nullptr, M, G, d_hi, d_lo, ldd, inv_norm, flags, xnorm, rank2,
                          drop_mode, stream);
+}
+
+// K1 straight into the operand format of the centroid paths (int8 limb planes + double scale, see limbs.cu):
+// no fp16 planes are written and no separate split pass runs.
+extern "C" int mn_rank_normalize_limbs(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index,
+                                       int64_t M, int32_t G, int8_t* a1, int8_t* a0, int64_t ldk, double* inv_norm64,
+                                       float* inv_norm, uint8_t* flags, int32_t drop_mode, mn_stream_t stream) {
+    MN_CHECK_ARG(X != nullptr && a1 != nullptr, "mn_rank_normalize_limbs: null pointer");
+    mn::CsrIn none = {nullptr, nullptr, nullptr};
+    return rank_dispatch(X, ldx, none, row_index, col_index, M, G, nullptr, nullptr, 0, inv_norm, flags, nullptr, nullptr,
+                         drop_mode, stream, mn::LimbOut{a1, a0, ldk, inv_norm64});
+}
+
+extern "C" int mn_rank_normalize_csr_limbs(const int64_t* indptr, const int32_t* indices, const float* data,
+                                           const int32_t* row_index, int64_t M, int32_t G, int8_t* a1, int8_t* a0,
+                                           int64_t ldk, double* inv_norm64, float* inv_norm, uint8_t* flags,
+                                           int32_t drop_mode, mn_stream_t stream) {
+    MN_CHECK_ARG(indptr && indices && data && a1, "mn_rank_normalize_csr_limbs: null pointer");
+    mn::CsrIn csr = {indptr, indices, data};
+    return rank_dispatch(nullptr, 0, csr, row_index, nullptr, M, G, nullptr, nullptr, 0, inv_norm, flags, nullptr, nullptr,
+                         drop_mode, stream, mn::LimbOut{a1, a0, ldk, inv_norm64});
 }

@@ -162,7 +162,7 @@ rank_warp_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
                  const int32_t* __restrict__ col_index, int64_t M, int G, int cap, int g_pad,
                  __half* __restrict__ d_hi, __half* __restrict__ d_lo, int64_t ldd, float* __restrict__ inv_norm,
                  uint8_t* __restrict__ flags, float* __restrict__ xnorm, int32_t* __restrict__ rank2, int drop_mode,
-                 int only_mask, CsrIn csr) {
+                 int only_mask, CsrIn csr, LimbOut limb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
@@ -268,9 +268,24 @@ rank_warp_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
             inv_norm[row] = drop ? 0.f : (float)inv_true;
             flags[row] = (uint8_t)((zerovar ? 1 : 0) | (nonpos ? 2 : 0) | (drop ? 4 : 0));
         }
+        if (limb.a1) {
+            uint32_t* p1 = reinterpret_cast<uint32_t*>(limb.a1 + row * limb.ldk);
+            uint32_t* p0 = reinterpret_cast<uint32_t*>(limb.a0 + row * limb.ldk);
+            const bool one_limb = G <= 127;
+            for (int g4 = lane; g4 < (int)(limb.ldk >> 2); g4 += 32) {
+                int d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d[u] = (!drop && 4 * g4 + u < G) ? (int)r2s[4 * g4 + u] - c : 0;
+                uint32_t w1, w0;
+                limb_pack4(d, one_limb, w1, w0);
+                p1[g4] = w1;
+                p0[g4] = w0;
+            }
+            if (lane == 0) limb.inv64[row] = drop ? 0.0 : inv_true;
+        }
         __half2* ph = reinterpret_cast<__half2*>(d_hi + row * ldd);
         __half2* pl = d_lo ? reinterpret_cast<__half2*>(d_lo + row * ldd) : nullptr;
-        for (int g2 = lane; g2 < (int)(ldd >> 1); g2 += 32) {
+        for (int g2 = lane; d_hi && g2 < (int)(ldd >> 1); g2 += 32) {
             const int g = 2 * g2;
             const int d0 = (!drop && g < G) ? (int)r2s[g] - c : 0;
             const int d1 = (!drop && g + 1 < G) ? (int)r2s[g + 1] - c : 0;
@@ -294,7 +309,8 @@ rank_warp_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __rest
 // returns 0 on success; *may_overflow tells the caller to run the CTA kernel on flagged rows
 int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* col_index, int64_t M, int G,
                      __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
-                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr) {
+                     int32_t* rank2, int drop_mode, cudaStream_t st, bool* may_overflow, int only_mask, CsrIn csr,
+                     LimbOut limb) {
     int cap = 64;
     while (cap < G && cap < RW_CAP) cap <<= 1;          // never more than the row can hold
     const int g_pad = (G + 7) & ~7;
@@ -312,7 +328,7 @@ int launch_rank_warp(const float* X, int64_t ldx, const int32_t* row_index, cons
     if (blocks > max_blocks) blocks = max_blocks;
     rank_warp_kernel<<<(unsigned)blocks, RW_WARPS * 32, smem, st>>>(X, ldx, row_index, col_index, M, G, cap, g_pad, d_hi,
                                                                   d_lo, ldd, inv_norm, flags, xnorm, rank2, drop_mode,
-                                                                  only_mask, csr);
+                                                                  only_mask, csr, limb);
     MN_LAUNCH_CHECK();
     return 0;
 }

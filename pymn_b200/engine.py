@@ -115,7 +115,9 @@ def to_device_matrix(X):
 
 @dataclass
 class RankedCells:
-    d_hi: torch.Tensor
+    """K1 output.  Full-network / test form: fp16 planes d_hi (+ d_lo beyond 2,048 genes).  Centroid-path form
+    (``rank_normalize(..., limbs=True)``): no planes, ``_limbs`` = (a1, a0, ldk, inv_norm64) int8 limb planes."""
+    d_hi: torch.Tensor | None
     d_lo: torch.Tensor | None
     ldd: int
     inv_norm: torch.Tensor
@@ -124,6 +126,11 @@ class RankedCells:
     G: int
     xnorm: torch.Tensor | None = None
     rank2: torch.Tensor | None = None
+    _limbs: tuple | None = None
+
+    @property
+    def device(self):
+        return self.inv_norm.device
 
 
 def alloc_ranked(M: int, G: int, dev) -> RankedCells:
@@ -136,10 +143,32 @@ def alloc_ranked(M: int, G: int, dev) -> RankedCells:
 
 
 def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
-                   want_xnorm=False, want_rank2=False, out: RankedCells = None, out_row0: int = 0) -> RankedCells:
+                   want_xnorm=False, want_rank2=False, out: RankedCells = None, out_row0: int = 0,
+                   limbs: bool = False) -> RankedCells:
     """K1.  X: float32 CUDA [N, Gx] row-major, or a CsrMatrix.  With ``out`` the M = len(row_index) cells are
     written into rows [out_row0, out_row0 + M) of preallocated outputs (the streamed pipeline ranks the
-    cells chunk by chunk as their rows arrive)."""
+    cells chunk by chunk as their rows arrive).  ``limbs``: write the int8 limb planes + double scale of the
+    centroid paths instead of the fp16 planes (mn_rank_normalize_limbs)."""
+    if limbs:
+        assert out is None and not want_xnorm and not want_rank2
+        is_csr = isinstance(X, CsrMatrix)
+        dev = X.data.device if is_csr else X.device
+        assert not (is_csr and col_index is not None), "column sub-setting of a CSR matrix is not supported"
+        M = int(row_index.numel()) if row_index is not None else int(X.shape[0])
+        G = int(col_index.numel()) if col_index is not None else int(X.shape[1])
+        ldk = (G + 127) // 128 * 128
+        a1 = torch.empty((M, ldk), dtype=torch.int8, device=dev)
+        a0 = torch.empty((M, ldk), dtype=torch.int8, device=dev)
+        inv64 = torch.empty((M,), dtype=torch.float64, device=dev)
+        inv_norm = torch.empty((M,), dtype=torch.float32, device=dev)
+        flags = torch.empty((M,), dtype=torch.uint8, device=dev)
+        if M > 0 and is_csr:
+            _lib.call("mn_rank_normalize_csr_limbs", X.indptr, X.indices, X.data, row_index, M, G, a1, a0, ldk, inv64,
+                      inv_norm, flags, int(drop_mode))
+        elif M > 0:
+            _lib.call("mn_rank_normalize_limbs", X, int(X.stride(0)), row_index, col_index, M, G, a1, a0, ldk, inv64,
+                      inv_norm, flags, int(drop_mode))
+        return RankedCells(None, None, (G + 63) // 64 * 64, inv_norm, flags, M, G, _limbs=(a1, a0, ldk, inv64))
     if out is not None:
         assert row_index is not None and col_index is None and not want_xnorm and not want_rank2
         M = int(row_index.numel())
@@ -194,13 +223,16 @@ def centroids_fixed(rc: RankedCells, row_off: torch.Tensor, L: int, extra_rows: 
     """K2, fixed-point form.  Returns (Cq int64 [L + extra_rows, ldd] = sum over the label's kept cells of
     x* rounded to multiples of 2^-38, nq int32 [L + extra_rows] kept cells): exact integer sums, so partial
     results of different GPUs add (all-reduce) to bit-identical centroids for every world size."""
-    dev = rc.d_hi.device
+    dev = rc.device
     Cq = torch.zeros((L + extra_rows, rc.ldd), dtype=torch.int64, device=dev)
     nq = torch.zeros((L + extra_rows,), dtype=torch.int32, device=dev)
     if rc.M > 0 and L > 0:
-        inv64 = cell_limbs(rc)[3]
-        _lib.call("mn_centroids_fixed", rc.d_hi, rc.d_lo, rc.ldd, inv64, row_off, L, rc.G,
-                  int(max_label_rows) if max_label_rows else rc.M, Cq, rc.ldd, nq)
+        a1, a0, ldk, inv64 = cell_limbs(rc)
+        mlr = int(max_label_rows) if max_label_rows else rc.M
+        if rc.d_hi is None:
+            _lib.call("mn_centroids_fixed_i8", a1, a0, ldk, inv64, row_off, L, rc.G, mlr, Cq, rc.ldd, nq)
+        else:
+            _lib.call("mn_centroids_fixed", rc.d_hi, rc.d_lo, rc.ldd, inv64, row_off, L, rc.G, mlr, Cq, rc.ldd, nq)
     return Cq, nq
 
 
@@ -243,7 +275,7 @@ def split_f16(C: torch.Tensor, G: int):
 def cell_limbs(rc: RankedCells):
     """int8 limb planes of the ranked cells (d = 128 a1 + a0) and their double-precision scale, cached on ``rc``."""
     if getattr(rc, "_limbs", None) is None:
-        dev = rc.d_hi.device
+        dev = rc.device
         ldk = (rc.G + 127) // 128 * 128
         a1 = torch.empty((rc.M, ldk), dtype=torch.int8, device=dev)
         a0 = torch.empty((rc.M, ldk), dtype=torch.int8, device=dev)
@@ -260,7 +292,7 @@ def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col
     through integer limb products on the int8 tensor cores; the epilogue works in double:
     val = x.c + addend;  with ``den`` (double [S, M]) val = val / den[col_den[n]] * col_scale[n] - 1, otherwise
     val -= col_scale[n].  Returns [Nn, max(M, ldo)] column-major, float32 (rounded once) or float64 (``as_double``)."""
-    dev = rc.d_hi.device
+    dev = rc.device
     a1, a0, ldk, inv64 = cell_limbs(rc)
     rows_pad = (Nn + 127) // 128 * 128
     limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
@@ -278,7 +310,7 @@ def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col
 
 def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int):
     """Node degree of every cell against the S study-centroid rows of C, in double: [S, M]."""
-    dev = rc.d_hi.device
+    dev = rc.device
     a1, a0, ldk, inv64 = cell_limbs(rc)
     q32 = torch.empty((S, ldk), dtype=torch.int32, device=dev)
     inv_scale = torch.empty((S,), dtype=torch.float32, device=dev)
@@ -399,7 +431,7 @@ def _device_matrix(X):
 
 def local_ranked_cells(Xd, base: int, sh: CellShard, drop_mode=0):
     """K1 over this rank's cells in local label-sorted order (``Xd`` row 0 = input row ``base``)."""
-    return rank_normalize(Xd, row_index=_i32(sh.rows - base), drop_mode=drop_mode)
+    return rank_normalize(Xd, row_index=_i32(sh.rows - base), drop_mode=drop_mode, limbs=True)
 
 
 def _column_reference(Xd, base: int, sh: CellShard, C: torch.Tensor, n_rows: int) -> torch.Tensor:
@@ -414,7 +446,7 @@ def _column_reference(Xd, base: int, sh: CellShard, C: torch.Tensor, n_rows: int
     ldd = int(C.stride(0))
     if b_hi > b_lo:
         rb = rank_normalize(Xd, row_index=torch.arange(b_lo - base, b_hi - base, dtype=torch.int32, device=dev),
-                            drop_mode=0)
+                            drop_mode=0, limbs=True)
         m = b_hi - b_lo
         nb = (m + 31) // 32
         off = torch.clamp(torch.arange(0, nb + 1, dtype=torch.int32, device=dev) * 32, max=m)
@@ -439,7 +471,7 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
     contest, so one all-to-all turns [all columns, own cells] into [own columns, all cells] (column j lives on
     rank j % world), and one all-gather assembles the L_test x L_train table.  Votes are exact integer dot
     products scaled in double, so every world size produces bit-identical tables."""
-    dev = rc.d_hi.device
+    dev = rc.device
     rank, world = sh.rank, sh.world
     n_lab = len(lay.row_labels)
     n_seg = len(lay.studies)
@@ -600,7 +632,7 @@ def us_pretrained_device(X, lay: LabelLayout, model_centroids, model_n, model_st
     if t: t.stop("rank_normalize")
     if t: t.start("centroids")
     Lt = int(model_centroids.shape[0])
-    dev = rc.d_hi.device
+    dev = rc.device
     C = torch.zeros((Lt + n_model_studies, rc.ldd), dtype=torch.float32, device=dev)
     C[:Lt, :rc.G] = (model_centroids if isinstance(model_centroids, torch.Tensor)
                      else to_device(np.asarray(model_centroids, np.float32)))
@@ -1046,7 +1078,7 @@ def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types:
     S = ctx.n_studies
     K = n_types
     Xd = ctx.Xd
-    rc = rank_normalize(Xd, row_index=ctx.perm, col_index=col_index, drop_mode=1 if fast else 0)
+    rc = rank_normalize(Xd, row_index=ctx.perm, col_index=col_index, drop_mode=1 if fast else 0, limbs=bool(fast))
     dev = Xd.device
     cell_label, cell_study = ctx.cell_label, ctx.cell_study
     vmat = torch.empty((K, rc.M), dtype=torch.float32, device=dev)

@@ -66,6 +66,61 @@ def test_rank_normalize_bit_exact(eng, n, g, kind):
     assert np.nanmax(np.abs(got - ref), initial=0.0) < 2e-7      # float32 rounding of a float64 result
 
 
+@pytest.mark.parametrize("n,g,kind", [
+    (64, 257, "counts"), (33, 2000, "counts"), (17, 3000, "counts"), (40, 50, "ties"), (9, 1, "counts"),
+    (30, 1000, "dense"), (12, 4096, "dense"), (25, 127, "ties"), (26, 128, "counts"), (5, 16000, "counts"),
+])
+@pytest.mark.parametrize("drop_mode", [0, 1])
+def test_rank_normalize_limb_output(eng, n, g, kind, drop_mode):
+    """K1 writing the int8 limb planes of the centroid paths directly (mn_rank_normalize_limbs, all three stages,
+    dense and CSR input, row / column gathers) = the fp16 planes put through mn_limb_split_cells, bit for bit."""
+    from scipy import sparse
+    rng = np.random.default_rng(n * 7919 + g + drop_mode)
+    x = _rand_matrix(rng, n, g, kind)
+    x[0] = 0.0
+    if n > 3:
+        x[3] = 7.0
+    if kind == "dense":
+        x[:, ::5] = 0.0
+    rows = eng._i32(rng.permutation(n).astype(np.int32))
+    Xd = eng.to_device(x)
+    ref = eng.rank_normalize(Xd, row_index=rows, drop_mode=drop_mode)
+    a1r, a0r, ldk, inv64r = eng.cell_limbs(ref)
+    for src in (Xd, eng.to_device_matrix(sparse.csr_matrix(x))):
+        got = eng.rank_normalize(src, row_index=rows, drop_mode=drop_mode, limbs=True)
+        a1, a0, ldk2, inv64 = eng.cell_limbs(got)
+        torch.cuda.synchronize()
+        assert got.d_hi is None and ldk2 == ldk
+        assert torch.equal(a1, a1r) and torch.equal(a0, a0r), "limb planes differ"
+        assert torch.equal(inv64, inv64r) and torch.equal(got.inv_norm, ref.inv_norm)
+        assert torch.equal(got.flags & 7, ref.flags & 7)
+    # the planes reassemble to the exact centred ranks: d = 128 a1 + a0
+    d = (1 if g <= 127 else 128) * a1r.cpu().numpy().astype(np.int64) + a0r.cpu().numpy().astype(np.int64)
+    keep = (ref.flags.cpu().numpy() & 4) == 0
+    want = O.rank2_rows(x[rows.cpu().numpy()]) - (g + 1)
+    assert np.array_equal(d[keep][:, :g], want[keep]) and not d[:, g:].any() and not d[~keep].any()
+    if g > 20:
+        cols = eng._i32(np.sort(rng.choice(g, size=g // 2, replace=False)).astype(np.int32))
+        ref = eng.rank_normalize(Xd, row_index=rows, col_index=cols, drop_mode=drop_mode)
+        got = eng.rank_normalize(Xd, row_index=rows, col_index=cols, drop_mode=drop_mode, limbs=True)
+        for u, v in zip(eng.cell_limbs(ref)[:2] + eng.cell_limbs(ref)[3:], eng.cell_limbs(got)[:2] + eng.cell_limbs(got)[3:]):
+            assert torch.equal(u, v)
+
+
+def test_centroids_from_limbs_equal_planes(eng):
+    """K2 on the limb planes (mn_centroids_fixed_i8) = K2 on the fp16 planes: the same integer sums."""
+    rng = np.random.default_rng(77)
+    for n, g, L in [(500, 300, 7), (333, 2500, 40), (64, 100, 3)]:
+        x = _rand_matrix(rng, n, g, "counts")
+        x[5] = 0
+        cuts = np.sort(rng.choice(np.arange(1, n), size=L - 1, replace=False))
+        row_off = eng._i32(np.concatenate([[0], cuts, [n]]).astype(np.int32))
+        Xd = eng.to_device(x)
+        a = eng.centroids_fixed(eng.rank_normalize(Xd), row_off, L, extra_rows=1)
+        b = eng.centroids_fixed(eng.rank_normalize(Xd, limbs=True), row_off, L, extra_rows=1)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
 def test_rank_normalize_golden_and_gather(eng):
     spec, inp, ref = C.load_case("normalize")
     x = inp["X"]
