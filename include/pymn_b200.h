@@ -100,6 +100,14 @@ int mn_rank_normalize_csr_limbs(const int64_t* indptr, const int32_t* indices, c
 int mn_gene_stats(const float* X, int64_t ldx, const int32_t* row_index, const int32_t* seg_off,
                   int32_t n_seg, int32_t G, double* median, double* variance, mn_stream_t stream);
 
+/* Columns of a sparse matrix in CSC form (indptr int64 [G + 1], indices int32 = row ids, data float32) expanded
+ * into a dense row-major tile: out[r, j] = X[r, cols[j]] (cols == NULL: columns col0 .. col0 + n_cols - 1), zero
+ * elsewhere; out float32 [N, ld], ld >= n_cols.  Feeds the gene-set slices of the supervised path
+ * (MetaNeighbor.py:84-93) and the per-gene statistics of variableGenes (variableGenes.py:109-135) from a sparse
+ * AnnData.X without densifying the matrix. */
+int mn_csc_gather_dense(const int64_t* indptr, const int32_t* indices, const float* data, const int32_t* cols,
+                        int32_t col0, int32_t n_cols, int64_t N, float* out, int64_t ld, mn_stream_t stream);
+
 /* ---- K2: cluster centroids ----------------------------------------------
  * Replaces X_norm @ onehot (MetaNeighborUS.py:284, trainModel.py:43,
  * MetaNeighbor.py:170 inner product) and n_cells_per_cluster (:288).
@@ -254,7 +262,9 @@ int mn_corr_vote(const mn_half_t* d_hi, const mn_half_t* d_lo, int64_t ldd, cons
 
 /* votes uint64 [N, L] + degree uint64 [N] -> float32 column-major [L, ldo] vote matrix.
  * Adds the diagonal (W_ii = 1, utils.py:74) to votes[i, label[i]] and degree[i];
- * ndn != 0 divides by the node degree (MetaNeighborUS.py:167-169). */
+ * ndn != 0 divides by the node degree (MetaNeighborUS.py:167-169).  degree == NULL: the node degree is taken as
+ * the row sum of votes (every voter carries a label) -- after a multi-GPU sum of the votes no second
+ * collective is needed for the degree. */
 int mn_votes_finalize(const uint64_t* votes, const uint64_t* degree, const int32_t* label, int64_t N,
                       int32_t L, int32_t ndn, float* out, int64_t ldo, mn_stream_t stream);
 

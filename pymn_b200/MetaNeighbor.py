@@ -96,7 +96,17 @@ def MetaNeighbor(
 
     study_vec = adata.obs[study_col].values
     ct_vec = adata.obs[ct_col].values
-    expression = to_dense_f32(adata[:, shared_genes].X)
+    # The reference slices `adata[:, shared_genes]` (MetaNeighbor.py:80-83), a host copy of the whole matrix in the
+    # sorted gene order.  Ranks and correlations do not depend on the order of the genes, so the matrix goes to
+    # the device as it is (dense, or CSC for a sparse X) and every gene set addresses its columns through the
+    # gene's position in adata.var_names; only a matrix with many more genes than the sets use is cut down first.
+    from scipy import sparse
+    var_pos = pd.Index(adata.var_names).get_indexer(shared_genes)
+    X = adata.X
+    if len(shared_genes) * 2 < adata.shape[1]:
+        X = adata[:, shared_genes].X
+        var_pos = np.arange(len(shared_genes))
+    expression = X if sparse.issparse(X) else to_dense_f32(X)
     lay, ct_names = joint_layout(study_vec, ct_vec)
     S, K = len(lay.studies), len(ct_names)
 
@@ -107,7 +117,7 @@ def MetaNeighbor(
     ctx = engine.supervised_prepare(expression, lay)
     # the gene columns of all of this rank's sets go up in one copy; the per-set tables stay on the device
     # until the end, so the host enqueues set j + 1 while the GPU still works on set j
-    col_lists = [np.flatnonzero(gs_values[:, j]).astype(np.int32) for j in mine]
+    col_lists = [var_pos[np.flatnonzero(gs_values[:, j])].astype(np.int32) for j in mine]
     offs = np.concatenate([[0], np.cumsum([len(c) for c in col_lists])]).astype(np.int64)
     all_cols = engine._i32(np.concatenate(col_lists) if col_lists else np.zeros(0, np.int32))
     # fast_version: a cell that is constant and non-zero over a gene set turns the reference's whole result

@@ -80,7 +80,8 @@ def metaNeighborUS_default(adata, study_col, ct_col, node_degree_normalization, 
     [train label, test label] in globally sorted label order, like the reference."""
     S = adata.obs[study_col].values         # numpy or pandas array; label_layout factorises either as it is
     C = adata.obs[ct_col].values
-    Xd = engine.start_upload(prepare_matrix(adata.X))          # the upload runs while the host encodes the labels
+    # the upload (and, on several GPUs, K1 + the plane exchange) runs while the host encodes the labels
+    Xd = engine.start_upload(prepare_matrix(adata.X), full_network=True)
     lay = label_layout(S, C)
     r = engine.us_default(Xd, lay, bool(node_degree_normalization))
     order = np.argsort(lay.sorted_pos)                       # row-order ids in globally sorted order

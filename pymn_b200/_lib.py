@@ -28,6 +28,7 @@ SIGNATURES = {
     "mn_rank_normalize_limbs": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mn_rank_normalize_csr_limbs": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "mn_gene_stats": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "mn_csc_gather_dense": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp]),
     "mn_centroids": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "mn_centroids_fixed": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp]),
     "mn_centroids_fixed_i8": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp]),

@@ -220,7 +220,13 @@ __global__ void votes_finalize_kernel(const unsigned long long* __restrict__ vot
     if (i >= N) return;
     const unsigned long long one = MN_W_ONE;
     const int li = label[i];
-    const double deg = (double)(degree[i] + one);
+    unsigned long long dsum = 0ull;
+    if (degree) {
+        dsum = degree[i];
+    } else {                                  // node degree = sum of the cell's votes over all labels
+        for (int l = 0; l < L; ++l) dsum += votes[i * L + l];
+    }
+    const double deg = (double)(dsum + one);
     const double inv_one = 1.0 / (double)MN_W_ONE;
     for (int l = 0; l < L; ++l) {
         unsigned long long v = votes[i * L + l];
@@ -381,7 +387,7 @@ int mn_split_f16(const float* in, int64_t ld, int32_t R, int32_t G, mn_half_t* h
 
 int mn_votes_finalize(const uint64_t* votes, const uint64_t* degree, const int32_t* label, int64_t N, int32_t L,
                       int32_t ndn, float* out, int64_t ldo, mn_stream_t stream) {
-    MN_CHECK_ARG(votes && degree && label && out && N >= 1 && L >= 1 && ldo >= N, "mn_votes_finalize: bad arguments");
+    MN_CHECK_ARG(votes && label && out && N >= 1 && L >= 1 && ldo >= N, "mn_votes_finalize: bad arguments");
     mn::votes_finalize_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const unsigned long long*>(votes), reinterpret_cast<const unsigned long long*>(degree),
         label, N, L, ndn, out, ldo);

@@ -96,6 +96,36 @@ class CsrMatrix:
     shape: tuple
 
 
+@dataclass
+class CscMatrix:
+    """Expression matrix in CSC form on the device (scipy.sparse.csc_matrix layout): column access for the
+    gene-set slices of the supervised path and the per-gene statistics of variableGenes."""
+    indptr: torch.Tensor       # int64 [n_cols + 1]
+    indices: torch.Tensor      # int32 [nnz] row ids
+    data: torch.Tensor         # float32 [nnz]
+    shape: tuple
+
+
+def to_device_csc(X) -> CscMatrix:
+    """scipy.sparse matrix -> CscMatrix (only the stored values cross PCIe)."""
+    csc = X.tocsc()
+    if not csc.has_canonical_format:
+        csc = csc.copy()
+        csc.sum_duplicates()
+    return CscMatrix(to_device(np.asarray(csc.indptr, dtype=np.int64)), to_device(np.asarray(csc.indices, dtype=np.int32)),
+                     to_device(np.asarray(csc.data, dtype=np.float32)), tuple(csc.shape))
+
+
+def csc_columns_dense(csc: CscMatrix, cols: torch.Tensor = None, col0: int = 0, n_cols: int = None) -> torch.Tensor:
+    """Dense float32 [N, g] tile of the columns ``cols`` (int32 device tensor) or [col0, col0 + n_cols)."""
+    g = int(cols.numel()) if cols is not None else int(n_cols)
+    N = int(csc.shape[0])
+    ld = (g + 3) // 4 * 4                       # rows stay 16-byte aligned for K1's 128-bit loads
+    out = torch.empty((N, ld), dtype=torch.float32, device=csc.data.device)
+    _lib.call("mn_csc_gather_dense", csc.indptr, csc.indices, csc.data, cols, int(col0), g, N, out, ld)
+    return out[:, :g] if ld != g else out
+
+
 def to_device_matrix(X):
     """Dense array / tensor -> float32 CUDA tensor; scipy.sparse matrix -> CsrMatrix (no densification:
     only the stored values cross PCIe)."""
@@ -209,10 +239,30 @@ def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
 
 def gene_stats(X, perm: np.ndarray, seg_off: np.ndarray):
     """Per-study per-gene median and variance (variableGenes.py:22-27).  X: dense host / device matrix
-    [N, G]; perm int32[N] sorts the cells by study, seg_off int32[S+1] are the study ranges of that order.
+    [N, G] or a scipy.sparse matrix; perm int32[N] sorts the cells by study, seg_off int32[S+1] are the study ranges of that order.
     Returns (median float64 [S, G], variance float64 [S, G]) on the host."""
+    from scipy import sparse
+    S = int(len(seg_off) - 1)
+    if sparse.issparse(X):
+        # sparse AnnData.X: CSC on the device, 512 genes at a time expanded into a dense tile (never the whole matrix)
+        csc = to_device_csc(X)
+        N, G = csc.shape
+        dev = csc.data.device
+        med = torch.empty((S, G), dtype=torch.float64, device=dev)
+        var = torch.empty((S, G), dtype=torch.float64, device=dev)
+        perm_d, seg_d = _i32(perm), _i32(seg_off)
+        step = 512
+        for c0 in range(0, G, step):
+            g = min(step, G - c0)
+            tile = csc_columns_dense(csc, None, c0, g)
+            m_c = torch.empty((S, g), dtype=torch.float64, device=dev)
+            v_c = torch.empty((S, g), dtype=torch.float64, device=dev)
+            _lib.call("mn_gene_stats", tile, int(tile.stride(0)), perm_d, seg_d, S, g, m_c, v_c)
+            med[:, c0:c0 + g] = m_c
+            var[:, c0:c0 + g] = v_c
+        return med.cpu().numpy(), var.cpu().numpy()
     Xd = to_device(X, torch.float32)
-    S, G = int(len(seg_off) - 1), int(Xd.shape[1])
+    G = int(Xd.shape[1])
     med = torch.empty((S, G), dtype=torch.float64, device=Xd.device)
     var = torch.empty((S, G), dtype=torch.float64, device=Xd.device)
     _lib.call("mn_gene_stats", Xd, int(Xd.stride(0)), _i32(perm), _i32(seg_off), S, G, med, var)
@@ -819,7 +869,7 @@ def network_from_ranked(rc: RankedCells, cell_label, seg_off, L, S, ndn=True, nb
     if t: t.stop("corr_vote")
     if reduce_fn is not None:
         reduce_fn(votes)
-        reduce_fn(degree)
+        degree = None                     # = row sums of the reduced votes (mn_votes_finalize): no second collective
     vmat = torch.empty((L, N), dtype=torch.float32, device=dev)
     _lib.call("mn_votes_finalize", votes, degree, cell_label, N, L, int(bool(ndn)), vmat, N)
     if t: t.start("auroc")
@@ -887,7 +937,7 @@ STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "16"))
 STREAM_DEV_CHUNKS = int(_os.environ.get("MN_STREAM_DEV_CHUNKS", "4"))     # row chunks of the passes; 0 = as many as uploads
 
 
-def start_upload(X):
+def start_upload(X, full_network: bool = False):
     """Begin moving the expression matrix to the device.  A large dense float32 matrix in PINNED host memory
     is sent in row chunks, last rows first, on a side stream (AsyncUpload): the full-network pipeline
     starts ranking and correlating the last cells while the first ones are still crossing PCIe
@@ -896,7 +946,12 @@ def start_upload(X):
     if (world > 1 and SHARD_UPLOAD and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
             and X.flags.c_contiguous and X.shape[0] >= 4 * world):
         lo, hi, per = shard_rows(X.shape[0], rank, world)
-        return ShardedUpload(to_device(X[lo:hi], torch.float32), lo, hi, tuple(X.shape), rank, world, per)
+        sh = ShardedUpload(to_device(X[lo:hi], torch.float32), lo, hi, tuple(X.shape), rank, world, per)
+        if full_network:
+            # K1 is row-wise and the plane exchange needs no labels: both run (input order) while the host
+            # still encodes the labels; ranked_cells_sharded only applies the label permutation afterwards
+            sh.gathered = _rank_and_gather(sh, 0)
+        return sh
     if (STREAM_CHUNKS > 1 and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
             and X.flags.c_contiguous and X.nbytes >= STREAM_MIN_BYTES):
         t = torch.from_numpy(X)
@@ -964,7 +1019,7 @@ def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins
                   cell_label, L, votes, degree, sl, t_k)
     if reduce_fn is not None:
         reduce_fn(votes)
-        reduce_fn(degree)
+        degree = None                     # = row sums of the reduced votes (mn_votes_finalize): no second collective
     vmat = torch.empty((L, N), dtype=torch.float32, device=dev)
     _lib.call("mn_votes_finalize", votes, degree, cell_label, N, L, int(bool(ndn)), vmat, N)
     auc, n_pos = auroc(vmat, L, None, None, seg_off, S, cell_label, L)
@@ -995,6 +1050,16 @@ class ShardedUpload:
     def __init__(self, X_local, lo, hi, shape, rank, world, per):
         self.X_local, self.lo, self.hi, self.shape = X_local, lo, hi, shape
         self.rank, self.world, self.per = rank, world, per
+        self.gathered = None          # (drop_mode, planes and scales of ALL cells in input order), see start_upload
+
+
+def _rank_and_gather(sh: "ShardedUpload", drop_mode: int):
+    """K1 on the own slice (input order) + all-gather of planes, scales and flags: (drop_mode, d_hi, d_lo, inv_norm,
+    flags, ldd) with row j = input cell j."""
+    rc_loc = rank_normalize(sh.X_local, drop_mode=drop_mode)
+    return (drop_mode, gather_rows(rc_loc.d_hi, sh.per, sh.world),
+            gather_rows(rc_loc.d_lo, sh.per, sh.world) if rc_loc.d_lo is not None else None,
+            gather_rows(rc_loc.inv_norm, sh.per, sh.world), gather_rows(rc_loc.flags, sh.per, sh.world), rc_loc.ldd)
 
 
 def ranked_cells_sharded(sh: ShardedUpload, lay: LabelLayout, drop_mode=0) -> RankedCells:
@@ -1002,16 +1067,13 @@ def ranked_cells_sharded(sh: ShardedUpload, lay: LabelLayout, drop_mode=0) -> Ra
     order), one NCCL all-gather makes the fp16 planes (0.8 GB at config 2, ~ms over NVLink instead of N x
     the matrix over PCIe) and scales available everywhere, and a row gather puts them into label-sorted
     order.  K1 is row-wise, so the planes are identical to the single-GPU ones."""
-    _rank, world, _ = dist_shard()
     N, G = sh.shape
-    per = sh.per
-    rc_loc = rank_normalize(sh.X_local, drop_mode=drop_mode)
+    g = sh.gathered if (sh.gathered is not None and sh.gathered[0] == drop_mode) else _rank_and_gather(sh, drop_mode)
+    sh.gathered = None
+    _, d_hi, d_lo, inv_norm, flags, ldd = g
     perm = to_device(np.asarray(lay.perm, dtype=np.int64))
-    d_hi = gather_rows(rc_loc.d_hi, per, world).index_select(0, perm)
-    d_lo = gather_rows(rc_loc.d_lo, per, world).index_select(0, perm) if rc_loc.d_lo is not None else None
-    inv_norm = gather_rows(rc_loc.inv_norm, per, world).index_select(0, perm)
-    flags = gather_rows(rc_loc.flags, per, world).index_select(0, perm)
-    return RankedCells(d_hi, d_lo, rc_loc.ldd, inv_norm, flags, N, G)
+    return RankedCells(d_hi.index_select(0, perm), d_lo.index_select(0, perm) if d_lo is not None else None, ldd,
+                       inv_norm.index_select(0, perm), flags.index_select(0, perm), N, G)
 
 
 def us_default_sharded(sh: ShardedUpload, lay: LabelLayout, L, S, ndn=True, nbins=DEFAULT_NBINS):
@@ -1044,7 +1106,7 @@ class SupervisedContext:
     """Everything the per-gene-set pipeline needs that does not depend on the gene set, resident in HBM:
     the expression matrix and the label arrays (uploading them again for every set costs four
     synchronous pageable copies per set)."""
-    Xd: torch.Tensor
+    Xd: torch.Tensor | None
     perm: torch.Tensor
     cell_label: torch.Tensor
     cell_study: torch.Tensor
@@ -1052,11 +1114,17 @@ class SupervisedContext:
     seg_off: torch.Tensor
     n_studies: int
     max_label_rows: int = 0
+    csc: CscMatrix | None = None       # sparse input: gene-set columns are expanded per set (csc_columns_dense)
 
 
 def supervised_prepare(X, lay: LabelLayout) -> SupervisedContext:
     """Upload the shared expression matrix and the label layout once (MetaNeighbor.py:80-83)."""
+    from scipy import sparse
     counts = np.diff(np.asarray(lay.lab_row_off))
+    if sparse.issparse(X):
+        return SupervisedContext(None, _i32(lay.perm), _i32(lay.cell_label), _i32(lay.cell_study),
+                                 _i32(lay.lab_row_off), _i32(lay.seg_off), len(lay.studies),
+                                 int(counts.max()) if len(counts) else 0, to_device_csc(X))
     return SupervisedContext(to_device(X, torch.float32), _i32(lay.perm), _i32(lay.cell_label), _i32(lay.cell_study),
                              _i32(lay.lab_row_off), _i32(lay.seg_off), len(lay.studies),
                              int(counts.max()) if len(counts) else 0)
@@ -1077,9 +1145,14 @@ def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types:
     ``spill``: (buffer, tiles) of the rho spill decided once per run (None = decide here)."""
     S = ctx.n_studies
     K = n_types
-    Xd = ctx.Xd
-    rc = rank_normalize(Xd, row_index=ctx.perm, col_index=col_index, drop_mode=1 if fast else 0, limbs=bool(fast))
-    dev = Xd.device
+    if ctx.csc is not None:
+        # sparse input: the set's columns as a dense [N, g] tile (the matrix itself never densifies)
+        rc = rank_normalize(csc_columns_dense(ctx.csc, col_index), row_index=ctx.perm, drop_mode=1 if fast else 0,
+                            limbs=bool(fast))
+    else:
+        rc = rank_normalize(ctx.Xd, row_index=ctx.perm, col_index=col_index, drop_mode=1 if fast else 0,
+                            limbs=bool(fast))
+    dev = rc.device
     cell_label, cell_study = ctx.cell_label, ctx.cell_study
     vmat = torch.empty((K, rc.M), dtype=torch.float32, device=dev)
     if fast:
@@ -1103,7 +1176,7 @@ def supervised_tables(ctx: SupervisedContext, all_cols: torch.Tensor, offs, n_ty
     nothing synchronises.  The rho spill of the full-network mode is sized once for the whole run (its size
     depends on N only; asking the driver for the free memory costs more than a gene set's kernels)."""
     n_sets = len(offs) - 1
-    dev = ctx.Xd.device
+    dev = ctx.perm.device
     S, K = ctx.n_studies, n_types
     N = int(ctx.perm.numel())
     tables = torch.empty((n_sets, S * K, K), dtype=torch.float64, device=dev)

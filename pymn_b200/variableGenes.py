@@ -14,6 +14,12 @@ from . import engine
 from .utils import _factorize_sorted, _stable_argsort_small, to_dense_f32
 
 
+def _matrix(X):
+    """A sparse AnnData.X stays sparse (CSC on the device, variableGenes.py:109-135); anything else dense float32."""
+    from scipy import sparse
+    return X if sparse.issparse(X) else to_dense_f32(X)
+
+
 def _select(median: np.ndarray, variance: np.ndarray) -> np.ndarray:
     """variableGenes.py:28-37 on one study's gene statistics."""
     bins = np.quantile(median, q=np.linspace(0, 1, 11), method="midpoint")
@@ -30,7 +36,7 @@ def _select(median: np.ndarray, variance: np.ndarray) -> np.ndarray:
 
 def compute_var_genes(adata, return_vect=True):
     """Variable genes of a single dataset (variableGenes.py:7-42)."""
-    X = to_dense_f32(adata.X)
+    X = _matrix(adata.X)
     n = X.shape[0]
     med, var = engine.gene_stats(X, np.arange(n, dtype=np.int32), np.array([0, n], dtype=np.int32))
     sel = _select(med[0], var[0])
@@ -46,7 +52,7 @@ def variableGenes(adata, study_col, return_vect=False):
     studies, codes = _factorize_sorted(adata.obs[study_col].values)
     perm = _stable_argsort_small(codes, len(studies)).astype(np.int32)
     seg_off = np.concatenate([[0], np.cumsum(np.bincount(codes, minlength=len(studies)))]).astype(np.int32)
-    med, var = engine.gene_stats(to_dense_f32(adata.X), perm, seg_off)
+    med, var = engine.gene_stats(_matrix(adata.X), perm, seg_off)
     genes = adata.var_names
     var_genes_mat = pd.DataFrame(index=genes)
     for k, study in enumerate(studies):

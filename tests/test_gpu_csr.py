@@ -65,3 +65,61 @@ def test_api_sparse_input_matches_dense():
         md = pymn_b200.trainModel(ad_d, "study_id", "cell_type")
         ms = pymn_b200.trainModel(ad_s, "study_id", "cell_type")
         assert np.array_equal(md.values, ms.values)
+
+
+def test_csc_column_tiles():
+    """mn_csc_gather_dense: a gene set's columns of a sparse matrix as a dense tile (explicit column list and range)."""
+    eng = _eng()
+    rng = np.random.default_rng(3)
+    x = rng.poisson(0.3, size=(257, 90)).astype(np.float32)
+    csc = eng.to_device_csc(sparse.csr_matrix(x))
+    cols = np.array([5, 0, 89, 17, 17, 42, 3], dtype=np.int32)
+    got = eng.csc_columns_dense(csc, eng._i32(cols)).cpu().numpy()
+    assert np.array_equal(got, x[:, cols])
+    assert np.array_equal(eng.csc_columns_dense(csc, None, 13, 50).cpu().numpy(), x[:, 13:63])
+
+
+def test_supervised_sparse_input_matches_dense():
+    """MetaNeighbor on a sparse AnnData.X (gene-set sub-setting through CSC column tiles, MetaNeighbor.py:80-93)
+    gives exactly the dense tables, in both modes; the gene sets address adata.var_names in their own order."""
+    import pandas as pd
+    import pymn_b200
+    from pymn_b200.synth import make_genesets
+    x, s, c = make_counts(33, 3, 300, 240, 5)
+    genes = np.array([f"g{i}" for i in range(240)], dtype=object)
+    inp = dict(X=x, study=s, ctype=c, genes=genes, hvg=np.ones(240, bool))
+    ad_d = make_adata(inp)
+    ad_s = make_adata(inp)
+    ad_s.X = sparse.csr_matrix(x)
+    gs = pd.DataFrame(make_genesets(7, 240, 6, 8, 100), index=genes[::-1].copy(), columns=[f"set{j}" for j in range(6)])
+    for fast in (True, False):
+        td = pymn_b200.MetaNeighbor(ad_d, "study_id", "cell_type", gs, fast_version=fast, save_uns=False)
+        ts = pymn_b200.MetaNeighbor(ad_s, "study_id", "cell_type", gs, fast_version=fast, save_uns=False)
+        assert list(td.index) == list(ts.index) and list(td.columns) == list(ts.columns)
+        assert np.array_equal(td.values, ts.values, equal_nan=True), f"fast={fast}"
+    # a gene universe much larger than the sets: the host cuts the matrix down first (same result)
+    small = gs.iloc[:60]
+    t1 = pymn_b200.MetaNeighbor(ad_d, "study_id", "cell_type", small, fast_version=True, save_uns=False)
+    t2 = pymn_b200.MetaNeighbor(ad_s, "study_id", "cell_type", small, fast_version=True, save_uns=False)
+    assert np.array_equal(t1.values, t2.values, equal_nan=True)
+
+
+def test_variable_genes_sparse_matches_dense():
+    """variableGenes on a sparse AnnData.X (variableGenes.py:109-135): per-gene medians / variances from CSC column
+    tiles equal the dense ones, hence the same gene selection."""
+    import pymn_b200
+    eng = _eng()
+    x, s, c = make_counts(35, 3, 500, 700, 4)
+    genes = np.array([f"g{i}" for i in range(700)], dtype=object)
+    inp = dict(X=x, study=s, ctype=c, genes=genes, hvg=np.ones(700, bool))
+    ad_d = make_adata(inp)
+    ad_s = make_adata(inp)
+    ad_s.X = sparse.csr_matrix(x)
+    vd = pymn_b200.variableGenes(ad_d, "study_id", return_vect=True)
+    vs = pymn_b200.variableGenes(ad_s, "study_id", return_vect=True)
+    assert np.array_equal(np.asarray(vd), np.asarray(vs))
+    n = x.shape[0]
+    perm, seg = np.arange(n, dtype=np.int32), np.array([0, n // 2, n], dtype=np.int32)
+    md, vd2 = eng.gene_stats(x, perm, seg)
+    ms, vs2 = eng.gene_stats(sparse.csc_matrix(x), perm, seg)
+    assert np.array_equal(md, ms) and np.array_equal(vd2, vs2)
