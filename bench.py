@@ -497,6 +497,10 @@ def run_ours(args):
     sp = dict(engine.LAST_SPILL)
 
     # ---- end to end through the public API, host buffers -------------------------
+    if os.environ.get("MN_BENCH_GC_FREEZE"):        # diagnostic only: take the bench's own heap out of the GC's sight
+        import gc
+        gc.collect()
+        gc.freeze()
     e2e_steps = max(1, min(args.steps, 5))
     page_s, tab = ctx.wall(lambda: api_call(adata_page), 1, e2e_steps)
     assert np.array_equal(tab.values, ref_tab), "API table (pageable) differs from the device-resident run"
@@ -506,6 +510,27 @@ def run_ours(args):
     adata_pin = _adata(Xh.numpy(), s_lab, c_lab, G)
     e2e_s, tab = ctx.wall(lambda: api_call(adata_pin), max(1, min(args.warmup, 2)), e2e_steps)
     e2e_calls_ms = list(ctx.last_wall_ms)
+    if os.environ.get("MN_BENCH_TRACE") and rank == 0:      # diagnostic: device timeline of one more API call
+        log, orig = [], _lib.call
+
+        def traced(name, *a):
+            t = time.perf_counter()
+            orig(name, *a)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            log.append((name, t, ev))
+        _lib.call = traced
+        torch.cuda.synchronize()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        api_call(adata_pin)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        _lib.call = orig
+        sys.stderr.write(f"traced e2e call: wall {1e3 * (t1 - t0):.1f} ms\n")
+        for name, t, ev in log:
+            sys.stderr.write(f"   {name:24s} host +{1e3 * (t - t0):7.2f} ms   device done +{ev0.elapsed_time(ev):7.2f} ms\n")
     assert np.array_equal(tab.values, ref_tab), "API table differs from the device-resident run"
     # (N > 1: every rank uploads its own 1/N slice of the matrix -- the total over ranks is the matrix once --
     #  plus the small label arrays on every rank)

@@ -13,7 +13,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import joint_layout, to_dense_f32
+from .utils import joint_layout, to_dense_f32, with_gc_paused
 
 
 def _dist_info():
@@ -63,6 +63,7 @@ def _reduce_over_studies(auc: np.ndarray, S: int, K: int) -> np.ndarray:
         return np.nanmean(diag, axis=0)
 
 
+@with_gc_paused
 def MetaNeighbor(
     adata,
     study_col,

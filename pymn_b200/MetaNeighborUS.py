@@ -11,7 +11,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, prepare_matrix, select_genes
+from .utils import label_layout, prepare_matrix, select_genes, with_gc_paused
 
 
 def _pvals(roc: np.ndarray, n_pos: np.ndarray, n_neg: np.ndarray) -> np.ndarray:
@@ -96,6 +96,7 @@ def metaNeighborUS_default(adata, study_col, ct_col, node_degree_normalization, 
     return tab
 
 
+@with_gc_paused
 def MetaNeighborUS(adata,
                    study_col,
                    ct_col,

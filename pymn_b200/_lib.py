@@ -83,7 +83,8 @@ def require_cuda():
 def _ptr(t):
     if t is None:
         return None
-    assert t.is_cuda and t.is_contiguous(), "device, contiguous tensors only"
+    # (a row-pitched matrix -- unit column stride, rows ld apart -- is fine: its pitch travels as an argument)
+    assert t.is_cuda and (t.is_contiguous() or (t.dim() == 2 and t.stride(1) == 1)), "device, contiguous tensors only"
     return t.data_ptr()
 
 

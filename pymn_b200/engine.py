@@ -217,7 +217,7 @@ def rank_normalize(X: torch.Tensor, row_index=None, col_index=None, drop_mode=0,
         assert col_index is None, "column sub-setting of a CSR matrix is not supported"
         dev = X.data.device
     else:
-        assert X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.is_contiguous()
+        assert X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.stride(1) == 1     # (rows may be pitched)
         dev = X.device
     M = int(row_index.numel()) if row_index is not None else int(X.shape[0])
     G = int(col_index.numel()) if col_index is not None else int(X.shape[1])

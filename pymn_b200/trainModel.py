@@ -5,9 +5,10 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, prepare_matrix, select_genes
+from .utils import label_layout, prepare_matrix, select_genes, with_gc_paused
 
 
+@with_gc_paused
 def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
     """Pretrains the centroid model consumed by ``MetaNeighborUS(trained_model=...)``.
 

@@ -24,9 +24,63 @@ def join_labels(x, y, replace_bar=False):
     return np.array([str(a) + "|" + str(b) for a, b in zip(x, y)], dtype=object)
 
 
+_POOL = None
+
+
+def _pool():
+    """A small persistent thread pool for the host-side label encoding (Arrow's hash kernels release the GIL;
+    starting threads per call costs as much as the work)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="pymn_b200-labels")
+    return _POOL
+
+
+def _arrow_encode_async(vec, n_slices=4):
+    """Start the dictionary encoding of an Arrow-backed pandas string array in slices on the pool; returns the list
+    of futures (each -> (int32 codes of the slice, its distinct values)) or None when ``vec`` is not Arrow-backed
+    or holds nulls."""
+    arr = getattr(vec, "_pa_array", None)
+    if arr is None:
+        return None
+    try:
+        import pyarrow as pa
+        if arr.null_count or not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
+            return None
+        flat = arr.combine_chunks() if isinstance(arr, pa.ChunkedArray) else arr
+    except Exception:
+        return None
+    n = len(flat)
+    k = n_slices if n >= 50_000 else 1
+    bounds = [n * i // k for i in range(k + 1)]
+
+    def work(i):
+        enc = flat.slice(bounds[i], bounds[i + 1] - bounds[i]).dictionary_encode()
+        return np.asarray(enc.indices.to_numpy(zero_copy_only=False), dtype=np.int32), enc.dictionary.to_pylist()
+    if k == 1:
+        class _Done:
+            def __init__(self, v):
+                self._v = v
+
+            def result(self):
+                return self._v
+        return [_Done(work(0))]
+    return [_pool().submit(work, i) for i in range(k)]
+
+
+def _arrow_finish(futures):
+    """Sorted distinct values (code-point order, as np.unique) and int32 codes from the slice encodings."""
+    parts = [f.result() for f in futures]
+    names = sorted(set().union(*[p[1] for p in parts]))
+    pos = {v: i for i, v in enumerate(names)}
+    codes = [np.asarray([pos[v] for v in d], dtype=np.int32)[c] if len(d) else c for c, d in parts]
+    return np.array(names, dtype=object), (np.concatenate(codes) if len(codes) > 1 else codes[0])
+
+
 def _factorize_sorted(vec):
     """Sorted unique values (Python / code-point order, as np.unique on object
-    or str arrays) and int64 codes.  ``vec``: numpy array, pandas Series or pandas array -- a pandas
+    or str arrays) and integer codes.  ``vec``: numpy array, pandas Series or pandas array -- a pandas
     string column is factorised as it is (Arrow dictionary encoding), without a detour through
     200,000 Python objects."""
     import pandas as pd
@@ -34,6 +88,9 @@ def _factorize_sorted(vec):
         vec = vec.values
     if not isinstance(vec, np.ndarray) and getattr(getattr(vec, "dtype", None), "name", "") == "category":
         vec = np.asarray(vec, dtype=object)
+    fut = _arrow_encode_async(vec)
+    if fut is not None:
+        return _arrow_finish(fut)
     # hash-factorise the N cells (O(N)), then sort only the handful of distinct values
     codes, uniq = pd.factorize(vec, sort=False)
     if (codes < 0).any():                      # missing values: the reference would stringify them ("nan")
@@ -53,7 +110,10 @@ def _factorize_sorted(vec):
 
 
 def _stable_argsort_small(codes: np.ndarray, n_values: int) -> np.ndarray:
-    """Stable argsort of non-negative integer codes < n_values; 16-bit keys take NumPy's O(N) radix sort."""
+    """Stable argsort of non-negative integer codes < n_values; 8- and 16-bit keys take NumPy's O(N) radix sort
+    (one / two counting passes)."""
+    if n_values <= 256:
+        return np.argsort(codes.astype(np.uint8), kind="stable")
     if n_values <= 32767:
         return np.argsort(codes.astype(np.int16), kind="stable")
     return np.argsort(codes, kind="stable")
@@ -88,31 +148,36 @@ class LabelLayout:
 
 
 def _factorize_two(a, b):
-    """The two obs columns are factorised side by side (the Arrow / pandas hash kernels release the GIL)."""
-    n = len(a)
-    if n < 100_000:
+    """The two obs columns are factorised side by side: Arrow-backed string columns in slices on the persistent
+    pool (the hash kernels release the GIL), anything else through pandas' hash tables on two threads."""
+    import pandas as pd
+    a = a.values if isinstance(a, pd.Series) else a
+    b = b.values if isinstance(b, pd.Series) else b
+    fa, fb = _arrow_encode_async(a), _arrow_encode_async(b)
+    if fa is not None and fb is not None:
+        return _arrow_finish(fa), _arrow_finish(fb)
+    if len(a) < 100_000:
         return _factorize_sorted(a), _factorize_sorted(b)
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=2) as ex:
-        fa, fb = ex.submit(_factorize_sorted, a), ex.submit(_factorize_sorted, b)
-        return fa.result(), fb.result()
+    ra, rb = _pool().submit(_factorize_sorted, a), _pool().submit(_factorize_sorted, b)
+    return ra.result(), rb.result()
 
 
 def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     (st_uniq, st_codes), (ct_uniq, ct_codes) = _factorize_two(study, ctype)
     n_ct = len(ct_uniq)
-    # (32-bit codes when they fit: the O(N) passes below are memory-bound on the host)
-    if len(st_uniq) * n_ct < (1 << 31):
-        st_codes, ct_codes = st_codes.astype(np.int32), ct_codes.astype(np.int32)
-    pair = st_codes * n_ct + ct_codes
-    # distinct (study, type) pairs, ascending, and each cell's index into them (O(N): the code space is small)
     n_codes = len(st_uniq) * n_ct
-    if n_codes <= max(4 * len(pair), 1 << 20):
-        present = np.bincount(pair, minlength=n_codes) > 0
-        pair_uniq = np.flatnonzero(present)
-        pair_codes = (np.cumsum(present) - 1)[pair]
+    # (32-bit codes when they fit: the O(N) passes below are memory-bound on the host)
+    if n_codes < (1 << 31):
+        st_codes, ct_codes = st_codes.astype(np.int32, copy=False), ct_codes.astype(np.int32, copy=False)
+    pair = st_codes * n_ct + ct_codes
+    # distinct (study, type) pairs, ascending, and how many cells each holds (O(N): the code space is small)
+    small_space = n_codes <= max(4 * len(pair), 1 << 20)
+    if small_space:
+        pair_cnt = np.bincount(pair, minlength=n_codes)
+        pair_uniq = np.flatnonzero(pair_cnt)
+        cnt_uniq = pair_cnt[pair_uniq]
     else:
-        pair_uniq, pair_codes = np.unique(pair, return_inverse=True)
+        pair_uniq, pair_codes, cnt_uniq = np.unique(pair, return_inverse=True, return_counts=True)
     st_of = pair_uniq // n_ct
     st_names = [s.replace("|", ".") for s in st_uniq.tolist()] if replace_bar else st_uniq.tolist()
     if replace_bar:
@@ -122,14 +187,20 @@ def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     # row order: study (sorted) major, joined label (sorted as a string) minor
     order = sorted(range(len(names)), key=lambda i: (int(st_of[i]), names[i]))
     order = np.asarray(order, dtype=np.int64)
-    rank_of_pair = np.empty(len(names), np.int32)
-    rank_of_pair[order] = np.arange(len(names), dtype=np.int32)
-    cell_label = rank_of_pair[pair_codes]
-    perm = _stable_argsort_small(cell_label, len(names))
+    n_lab = len(names)
+    rank_of_pair = np.empty(n_lab, np.int32)
+    rank_of_pair[order] = np.arange(n_lab, dtype=np.int32)
+    if small_space:
+        # one gather through a table over the code space: pair code -> row-order label id
+        lut = np.zeros(n_codes, np.int32)
+        lut[pair_uniq] = rank_of_pair
+        cell_label = lut[pair]
+    else:
+        cell_label = rank_of_pair[pair_codes]
+    perm = _stable_argsort_small(cell_label, n_lab)
     row_labels = names[order]
     label_study = st_of[order].astype(np.int32)
-    n_lab = len(names)
-    counts = np.bincount(cell_label, minlength=n_lab)
+    counts = cnt_uniq[order]                   # cells per row-order label: no further pass over the cells
     lab_row_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     n_st = len(st_uniq)
     seg_lab_off = np.searchsorted(label_study, np.arange(n_st + 1)).astype(np.int32)
@@ -137,10 +208,11 @@ def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
     glob = sorted(range(n_lab), key=lambda i: row_labels[i])
     sorted_pos = np.empty(n_lab, np.int64)
     sorted_pos[np.asarray(glob, dtype=np.int64)] = np.arange(n_lab)
-    cell_label_sorted = cell_label[perm].astype(np.int32)
+    # the sorted order is label 0 repeated counts[0] times, label 1 ...: written sequentially, not gathered
+    cell_label_sorted = np.repeat(np.arange(n_lab, dtype=np.int32), counts)
     return LabelLayout(studies=st_uniq, row_labels=row_labels, perm=perm.astype(np.int32),
                        cell_label=cell_label_sorted,
-                       cell_study=label_study[cell_label_sorted].astype(np.int32),
+                       cell_study=np.repeat(label_study, counts),
                        seg_off=seg_off, lab_row_off=lab_row_off, seg_lab_off=seg_lab_off,
                        label_study=label_study, sorted_pos=sorted_pos)
 
@@ -165,6 +237,38 @@ def joint_layout(study, ctype):
                       label_study=np.repeat(np.arange(S), K).astype(np.int32),
                       sorted_pos=np.arange(S * K, dtype=np.int64))
     return lay, ct_uniq
+
+
+class gc_paused:
+    """Pause Python's cyclic garbage collector for the duration of one API call.  The call allocates a few
+    thousand short-lived containers (label factorisation, DataFrames); when that trips a full collection, the
+    collector walks the CALLER's whole heap -- with a few million label strings alive (the obs columns of the
+    very AnnData being scored) that is 10-20 ms, a fifth of the GPU work of a 200,000-cell call.  Nothing in the
+    call creates reference cycles worth collecting early; the previous state is restored on exit."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        if self._was:
+            gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        if self._was:
+            import gc
+            gc.enable()
+        return False
+
+
+def with_gc_paused(fn):
+    """Decorator form of gc_paused for the public entry points (signature and docstring preserved)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with gc_paused():
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def select_genes(adata, var_genes):
