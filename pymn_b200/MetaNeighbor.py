@@ -13,7 +13,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import joint_layout, to_dense_f32, with_gc_paused
+from .utils import check_gene_count, joint_layout, to_dense_f32, with_gc_paused
 
 
 def _dist_info():
@@ -80,6 +80,8 @@ def MetaNeighbor(
     lives densely in HBM here)."""
     assert study_col in adata.obs_keys(), "Study Col not in adata"
     assert ct_col in adata.obs_keys(), "Cluster Col not in adata"
+    # (the reference's two "is a floating point" asserts, MetaNeighbor.py:56-61, are `assert ~isinstance(...)`:
+    #  `~True` is -2 and `~False` is -1, both truthy -- they can never fire, so there is nothing to reproduce)
     assert (
         pd.unique(adata.obs[study_col].values).shape[0] > 1
     ), f"Found only 1 unique study_id in {study_col}"
@@ -93,6 +95,7 @@ def MetaNeighbor(
     genesets = genesets.loc[:, genesets.sum() > 0]
 
     assert genesets.shape[1] > 0, "All Genesets are empty"
+    check_gene_count(int(genesets.values.sum(axis=0).max()), "genes per gene set")
     genesets = genesets.astype(bool)
 
     study_vec = adata.obs[study_col].values

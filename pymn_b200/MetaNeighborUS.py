@@ -11,7 +11,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, prepare_matrix, select_genes, with_gc_paused
+from .utils import check_gene_count, label_layout, prepare_matrix, select_genes, with_gc_paused
 
 
 def _pvals(roc: np.ndarray, n_pos: np.ndarray, n_neg: np.ndarray) -> np.ndarray:
@@ -125,6 +125,7 @@ def MetaNeighborUS(adata,
         var_genes = adata.var_names[np.isin(adata.var_names, var_genes)]
 
     assert var_genes.shape[0] > 2, "Must have at least 2 genes"
+    check_gene_count(var_genes.shape[0])
     if var_genes.shape[0] < 5:
         warnings.warn("You should have at least 5 Variable Genes", category=UserWarning)
     if one_vs_best:

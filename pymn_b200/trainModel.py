@@ -5,7 +5,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine
-from .utils import label_layout, prepare_matrix, select_genes, with_gc_paused
+from .utils import check_gene_count, label_layout, prepare_matrix, select_genes, with_gc_paused
 
 
 @with_gc_paused
@@ -25,6 +25,7 @@ def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
     else:
         var_genes = adata.var_names[np.asarray(adata.var[var_genes].values, dtype=bool)]
     assert var_genes.shape[0] > 2, "Must have at least 2 genes"
+    check_gene_count(var_genes.shape[0])
 
     sub = select_genes(adata, var_genes)
     X = engine.start_upload(prepare_matrix(sub.X))       # the upload runs while the host encodes the labels

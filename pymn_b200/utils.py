@@ -271,6 +271,17 @@ def with_gc_paused(fn):
     return wrapper
 
 
+MAX_GENES = 16384
+
+
+def check_gene_count(n_genes: int, what: str = "selected genes"):
+    """The rank kernels index genes with 16 bits: more than 16,384 genes per cell cannot be ranked in one call.
+    The reference has no such limit (it is 100-1000x slower there, but it runs): fail early and clearly."""
+    if int(n_genes) > MAX_GENES:
+        raise ValueError(f"pymn_b200 ranks at most {MAX_GENES} {what} per cell (got {int(n_genes)}); "
+                         "select highly variable genes first (pymn_b200.variableGenes)")
+
+
 def select_genes(adata, var_genes):
     """``adata[:, var_genes]`` -- except that selecting every gene in its own order returns ``adata`` itself:
     AnnData (and AnnDataLite) materialise a view's ``X`` as a copy, 1.6 GB of host traffic at config 2 for

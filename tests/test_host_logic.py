@@ -200,3 +200,16 @@ def test_label_layout_randomised_against_plain_python(seed, kind):
     assert lay.seg_off[-1] == n and lay.lab_row_off[-1] == n
     for t in range(len(st_sorted)):
         assert set(lay.cell_study[lay.seg_off[t]:lay.seg_off[t + 1]].tolist()) <= {t}
+
+
+def test_gene_count_limit_is_reported_early():
+    """More than 16,384 selected genes: a clear ValueError at the API instead of a failure deep inside the library."""
+    import pymn_b200
+    from pymn_b200.anndata_lite import AnnDataLite
+    G = 16385
+    ad = AnnDataLite(np.zeros((4, G), np.float32), pd.DataFrame({"s": ["a", "a", "b", "b"], "c": ["x", "y", "x", "y"]}),
+                     pd.DataFrame({"highly_variable": np.ones(G, bool)}, index=[f"g{i}" for i in range(G)]))
+    with pytest.raises(ValueError, match="16384"):
+        pymn_b200.MetaNeighborUS(ad, "s", "c", fast_version=True)
+    with pytest.raises(ValueError, match="16384"):
+        pymn_b200.trainModel(ad, "s", "c")
