@@ -322,6 +322,23 @@ int mn_one_vs_best(const float* votes, int64_t ldv, int32_t ncols, const float* 
                    const int32_t* lab_row_off, const int32_t* cell_label, int32_t n_labels,
                    const double* auroc, double* out, mn_stream_t stream);
 
+/* ---- supervised MetaNeighbor, fast_version: all gene sets of one rank in one call --------------------------
+ * Replaces the per-gene-set loop of MetaNeighbor.py:84-93 over score_low_mem (:106-148) / compute_votes (:151-176):
+ * for each set j (gene columns all_cols[set_off[j] .. set_off[j+1]) of X, at most g_max of them) the host loop --
+ * in C, no interpreter or FFI cost per set -- enqueues mn_rank_normalize_limbs (drop_mode 1, cells gathered through
+ * perm into joint (study, type) order) -> mn_centroids_fixed_i8 / _finish over the S*K joint labels ->
+ * mn_limb_split_centroids + mn_votes_fast_i8 -> mn_loso_finalize -> mn_mask_dropped -> mn_auroc.
+ *   X float32 [*, ldx] device; perm, lab_row_off [S*K+1], cell_label, cell_study, seg_off [S+1]: device int32
+ *   all_cols: device int32; set_off_host: HOST int64 [n_sets + 1]
+ *   tables: device float64 [n_sets, S*K, K] (rows = joint test labels); poison: device uint8 [n_sets]
+ *   workspace: device, mn_supervised_fast_workspace_bytes(N, g_max, S, K) bytes.  Nothing synchronises. */
+int64_t mn_supervised_fast_workspace_bytes(int64_t N, int32_t g_max, int32_t S, int32_t K);
+int mn_supervised_fast_sets(const float* X, int64_t ldx, const int32_t* perm, int64_t N, const int32_t* all_cols,
+                            const int64_t* set_off_host, int32_t n_sets, int32_t g_max, const int32_t* lab_row_off,
+                            const int32_t* cell_label, const int32_t* cell_study, const int32_t* seg_off, int32_t S,
+                            int32_t K, int32_t ndn, int64_t max_label_rows, void* workspace, int64_t workspace_bytes,
+                            double* tables, uint8_t* poison, mn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,9 @@ SIGNATURES = {
     "mn_votes_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "mn_mask_dropped": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mn_loso_finalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "mn_supervised_fast_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
+    "mn_supervised_fast_sets": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
+                                          _i64, _vp, _i64, _vp, _vp, _vp]),
     "mn_auroc_workspace_bytes": (_i64, [_i32, _i64, _i32, _i32]),
     "mn_auroc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _i64, _vp]),
     "mn_one_vs_best": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -114,6 +117,13 @@ def corr_spill_layout(n: int, row0: int, row1: int, shard_rank: int, shard_world
     if rc != 0:
         raise RuntimeError(f"mn_corr_spill_layout failed (rc={rc}): {lib.mn_last_error().decode()}")
     return int(nt.value), int(tb.value)
+
+
+def supervised_fast_workspace_bytes(n: int, g_max: int, s: int, k: int) -> int:
+    v = int(load().mn_supervised_fast_workspace_bytes(n, g_max, s, k))
+    if v < 0:
+        raise RuntimeError("mn_supervised_fast_workspace_bytes: bad shape")
+    return v
 
 
 def auroc_workspace_bytes(ncols: int, m: int, n_seg: int, n_labels: int) -> int:

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 OUT=../libpymn_b200.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
-SRCS="lib rank_normalize rank_warp rank_count centroids limbs auroc auroc_count gemm_tcgen05 gene_stats sparse"
+SRCS="lib rank_normalize rank_warp rank_count centroids limbs auroc auroc_count gemm_tcgen05 gene_stats sparse supervised"
 mkdir -p build
 pids=()
 for f in $SRCS; do

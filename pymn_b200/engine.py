@@ -1181,6 +1181,16 @@ def supervised_tables(ctx: SupervisedContext, all_cols: torch.Tensor, offs, n_ty
     N = int(ctx.perm.numel())
     tables = torch.empty((n_sets, S * K, K), dtype=torch.float64, device=dev)
     poison = torch.zeros((max(1, n_sets),), dtype=torch.uint8, device=dev)
+    if fast and n_sets > 0 and ctx.csc is None:
+        # one C-ABI call for all sets: the host loop over the sets runs in C (mn_supervised_fast_sets)
+        offs64 = np.ascontiguousarray(np.asarray(offs, dtype=np.int64))
+        g_max = int(np.diff(offs64).max())
+        wbytes = _lib.supervised_fast_workspace_bytes(N, g_max, S, K)
+        ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+        _lib.call("mn_supervised_fast_sets", ctx.Xd, int(ctx.Xd.stride(0)), ctx.perm, N, all_cols,
+                  int(offs64.ctypes.data), n_sets, g_max, ctx.lab_row_off, ctx.cell_label, ctx.cell_study, ctx.seg_off,
+                  S, K, int(bool(ndn)), int(ctx.max_label_rows), ws, wbytes, tables, poison)
+        return tables, poison
     spill = None
     if not fast and n_sets > 0:
         spill = rho_spill_buffer(N, 0, 1, nbins, dev, reserve_bytes=N * (S * K + 1) * 8 + N * K * 4 + (2 << 30))
