@@ -206,6 +206,14 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
                      const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
                      const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
                      mn_stream_t stream);
+/* Node degree on the int8 tensor cores, FULLY exact: den[s, m] = inv_norm64[m] * inv_scale[s] * sum_g d[m, g] q[s, g]
+ * + addend[s] for the S study-centroid rows whose limbs are b_limbs (mn_limb_split_centroids): the seven digit
+ * products of mn_votes_fast_i8 plus, in a second launch that adds into `out`, the weight-1 product a0 * b0 that the
+ * vote GEMM leaves out (a denominator shared by every train column of a study is worth the exact value).  Same result
+ * as mn_votes_den64 up to the last bit of a double; out: double [S, ldo]. */
+int mn_votes_den_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                    const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale, const float* addend,
+                    int32_t S, int32_t G, double* out, int64_t ldo, mn_stream_t stream);
 
 /* ---- K4/K5: full cell x cell network, never materialised -----------------
  * Replaces create_nw_spearman + rank (utils.py:35-75: np.corrcoef, one ranking

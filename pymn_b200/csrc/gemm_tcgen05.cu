@@ -65,6 +65,8 @@ struct GemmParams {
     int cls_first[MAX_TERMS];     // 1 = first term of its class: its first MMA overwrites the accumulator
     int b_limb_rows;
     int cls_mul;                  // weight of accumulator slot 0 (128 with two limbs of A, 1 with one)
+    int n_cls;                    // accumulator slots in use (4; 1 for the lone a0 * b0 product of mn_votes_den_i8)
+    int acc64;                    // 1: out64 += val instead of out64 = val
     const double* inv_a64;        // [M] exact-ish row scale 1/||d|| (double)
     // ... its epilogue, all in double:  val = dot * inv_a64[m] * inv_b[n] + addend[n];
     //   den != null:  val = val / den[col_den[n] * ld_den + m] * col_scale[n] - 1     (node-degree ratio, centred)
@@ -573,7 +575,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     constexpr int B_ROWS = BN / (PAIR ? 2 : 1);    // rows of the B tile this CTA stages
     constexpr uint32_t A_BYTES = BM * BK * 2;
     constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    // int8 form: one stage holds BOTH limb tiles of A and ALL FOUR digit tiles of B for one k-block; the (up to) seven
+    // digit products are issued from that one stage, so every operand byte is staged once per k-block (the
+    // term-major order of the fp16 form would stage 7 x (A + B) = 2.3x as much -- and the kernel is bound by
+    // shared-memory bandwidth: TMA writes + MMA operand reads)
+    constexpr uint32_t STAGE_BYTES = I8 ? (2 * A_BYTES + 4 * B_BYTES) : (A_BYTES + B_BYTES);
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0u;                     // cluster leader: claims tiles
     const uint32_t pair_rank = cta_rank & 1u;               // rank inside the CTA pair
@@ -714,6 +720,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 it.advance(tile - cur_tile);
                 cur_tile = tile;
                 const int m0 = it.mt * (BM * CTAS) + (int)cta_rank * BM, n0 = it.nt() * BN + (int)pair_rank * B_ROWS;
+                if constexpr (I8) {
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        unsigned char* sa = ring + (size_t)s * STAGE_BYTES;
+                        if constexpr (PAIR) {
+                            if (pair_leader) mbar_expect_tx(&full_bar[s], STAGE_BYTES * 2);
+                            tma_load_2d_pair(sa, &tm_a_hi, &full_bar[s], kb * BKE, m0);
+                            tma_load_2d_pair(sa + A_BYTES, &tm_a_lo, &full_bar[s], kb * BKE, m0);
+#pragma unroll
+                            for (int d = 0; d < 4; ++d)
+                                tma_load_2d_pair(sa + 2 * A_BYTES + d * B_BYTES, &tm_b_hi, &full_bar[s], kb * BKE,
+                                                 n0 + d * p.b_limb_rows);
+                        } else {
+                            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                            tma_load_2d(sa, &tm_a_hi, &full_bar[s], kb * BKE, m0);
+                            tma_load_2d(sa + A_BYTES, &tm_a_lo, &full_bar[s], kb * BKE, m0);
+#pragma unroll
+                            for (int d = 0; d < 4; ++d)
+                                tma_load_2d(sa + 2 * A_BYTES + d * B_BYTES, &tm_b_hi, &full_bar[s], kb * BKE,
+                                            n0 + d * p.b_limb_rows);
+                        }
+                        if (++s == p.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    continue;
+                }
                 for (int term = 0; term < p.n_terms; ++term) {
                     const CUtensorMap* ma = p.a_sel[term] ? &tm_a_lo : &tm_a_hi;
                     const CUtensorMap* mb = (!I8 && p.b_sel[term]) ? &tm_b_lo : &tm_b_hi;
@@ -762,8 +796,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (tile < 0) break;
                 mbar_wait(&tempty_bar[a], aph ^ 1u);
                 tc_fence_after();
+                if constexpr (I8) {
+                    // k-block-major: all digit products of a k-block from one stage; accumulator = weight class
+                    for (int kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(ring + (size_t)s * STAGE_BYTES);
+                        const int k_steps = (kb == p.k_blocks - 1) ? p.k_last : BK / UMMA_K;
+                        for (int term = 0; term < p.n_terms; ++term) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(a * ACC_COLS + p.cls[term] * BN);
+                            const bool fresh = (kb == 0 && p.cls_first[term] != 0);
+                            const uint64_t adesc = make_smem_desc(sa + (uint32_t)p.a_sel[term] * A_BYTES);
+                            const uint64_t bdesc = make_smem_desc(sa + 2 * A_BYTES + (uint32_t)p.b_sel[term] * B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                if (k >= k_steps) break;
+                                const uint32_t accum = (!fresh || k > 0) ? 1u : 0u;
+                                if constexpr (PAIR) tc_mma_i8_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                                else tc_mma_i8(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                            }
+                        }
+                        if constexpr (PAIR) tc_commit_pair(&empty_bar[s], slot_mask);
+                        else tc_commit(&empty_bar[s]);
+                        if (++s == p.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                }
                 int kb = 0, term = 0;
-                for (int i = 0; i < n_iters; ++i) {
+                for (int i = 0; i < (I8 ? 0 : n_iters); ++i) {
                     // fp16 form: k-blocks dealt round-robin to the NCHAIN accumulators; int8 form: accumulator = weight class
                     const int chain = I8 ? p.cls[term] : (i % NCHAIN);
                     const bool fresh = I8 ? (kb == 0 && p.cls_first[term] != 0) : (i < NCHAIN);
@@ -881,12 +943,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 for (int c0 = cbeg; c0 < cbeg + HALF_COLS; c0 += 32) {
                     long long v[32];
                     uint32_t r[32];
-                    tmem_ld32(t_base + (uint32_t)(c0 + 3 * BN), r);
+                    tmem_ld32(t_base + (uint32_t)(c0 + (p.n_cls - 1) * BN), r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] = (long long)(int)r[c];
 #pragma unroll
                     for (int cl = 2; cl >= 0; --cl) {
+                        if (cl >= p.n_cls - 1) continue;
                         tmem_ld32(t_base + (uint32_t)(c0 + cl * BN), r);
                         tmem_ld_wait();
 #pragma unroll
@@ -915,7 +978,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                 } else {
                                     val -= s_scale64[c0 + c];
                                 }
-                                if (p.out64) p.out64[n * p.ldo + m] = val;
+                                if (p.out64) p.out64[n * p.ldo + m] = p.acc64 ? p.out64[n * p.ldo + m] + val : val;
                                 else p.out[n * p.ldo + m] = (float)val;
                             }
                         }
@@ -1447,7 +1510,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, int64_t lda, int64_t 
     p.k_last = (G - (p.k_blocks - 1) * BKE + KSTEP - 1) / KSTEP;
     p.n_tiles = (int)((N + BN - 1) / BN);
     if (p.band <= 0) p.band = gemm_band() / CTAS;
-    const size_t stage_bytes = (size_t)(BM + B_BOX) * BK * 2;
+    const size_t stage_bytes = I8 ? (size_t)(2 * BM + 4 * B_BOX) * BK * 2 : (size_t)(BM + B_BOX) * BK * 2;
     const size_t table = (EPI == EPI_STORE) ? 0 : (size_t)((p.nbins + 2 + 3) & ~3) * 4;
     const size_t fixed = table + (size_t)BN * 12 + (size_t)EW * (BN / 2) * 4 + EW * 4 +
                          (2 * MAX_STAGES + 4 + 2 * TQ) * 8 + TQ * 4 + 16;
@@ -1543,7 +1606,7 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
     return launch_gemm<128, EPI_STORE, 4>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
 }
 
-int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+static int votes_i8(int low_only, const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
                      const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
                      const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
                      const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
@@ -1559,7 +1622,18 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
     GemmParams p;
     memset(&p, 0, sizeof(p));
     bool seen[4] = {false, false, false, false};
-    if (G <= 127) {
+    p.n_cls = 4;
+    if (low_only) {
+        // the weight-1 product a0 * b0 alone, added to what out64 already holds (mn_votes_den_i8)
+        p.a_sel[0] = 1;
+        p.b_sel[0] = 3;
+        p.cls[0] = 0;
+        p.cls_first[0] = 1;
+        p.n_terms = 1;
+        p.cls_mul = 1;
+        p.n_cls = 1;
+        p.acc64 = 1;
+    } else if (G <= 127) {
         // one limb of A (a1 = d itself, weight 1): the four products a1 * b3 .. b0 are the whole dot product
         for (int t = 0; t < 4; ++t) {
             p.a_sel[t] = 0;
@@ -1585,10 +1659,17 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
         p.n_terms = 7;
         p.cls_mul = 128;
     }
+    // CTA pairs (cta_group::2, 256 x 128 tiles: each CTA stages its own 128 rows of A and HALF of every B digit
+    // tile) when there are enough row tiles to keep every pair busy; MN_I8_CTAS=1 / 2 forces a form
+    int ctas = (M >= (int64_t)2 * BM * sm_count()) ? 2 : 1;
+    if (const char* e = getenv("MN_I8_CTAS")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2) ctas = v;
+    }
     p.b_limb_rows = b_limb_rows;
     p.tri = 0;
     p.mt0 = 0;
-    p.mt1 = (int)((M + BM - 1) / BM);
+    p.mt1 = (int)((M + BM * ctas - 1) / (BM * ctas));
     p.mt_step = 1;
     p.inv_a64 = inv_norm64;
     p.inv_b = inv_scale;
@@ -1600,7 +1681,29 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
     p.col_den = col_den;
     p.col_scale = col_scale;
     p.ldo = ldo;
+    if (ctas == 2)
+        return launch_gemm<128, EPI_STORE, 4, 2, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
     return launch_gemm<128, EPI_STORE, 4, 1, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
+}
+
+int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                     const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
+                     const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
+                     const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
+                     mn_stream_t stream) {
+    return votes_i8(0, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, addend, Nn, G, out, out64, ldo, den,
+                    ld_den, col_den, col_scale, stream);
+}
+
+int mn_votes_den_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                    const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale, const float* addend,
+                    int32_t S, int32_t G, double* out, int64_t ldo, mn_stream_t stream) {
+    MN_CHECK_ARG(out != nullptr, "mn_votes_den_i8: null output");
+    int rc = votes_i8(0, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, addend, S, G, nullptr, out, ldo,
+                      nullptr, 0, nullptr, nullptr, stream);
+    if (rc || G <= 127) return rc;          // one digit per rank: the four products above are the whole dot product
+    return votes_i8(1, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, nullptr, S, G, nullptr, out, ldo,
+                    nullptr, 0, nullptr, nullptr, stream);
 }
 
 static int corr_terms(mn::GemmParams& p, bool has_lo) {

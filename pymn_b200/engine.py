@@ -358,16 +358,26 @@ def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col
     return out
 
 
-def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int):
-    """Node degree of every cell against the S study-centroid rows of C, in double: [S, M]."""
+def votes_den64(rc: RankedCells, C: torch.Tensor, addend, S: int, cuda_cores: bool = False):
+    """Node degree of every cell against the S study-centroid rows of C, in double: [S, M].  Exact integer dot
+    products either way: all eight digit products on the int8 tensor cores (mn_votes_den_i8, the product path) or
+    64-bit integer FMAs on the CUDA cores (mn_votes_den64, ``cuda_cores`` / MN_DEN_CUDA_CORES=1: the A/B reference)."""
     dev = rc.device
     a1, a0, ldk, inv64 = cell_limbs(rc)
-    q32 = torch.empty((S, ldk), dtype=torch.int32, device=dev)
     inv_scale = torch.empty((S,), dtype=torch.float32, device=dev)
-    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), S, rc.G, None, ldk, S, inv_scale, q32)
     out = torch.empty((S, max(rc.M, 1)), dtype=torch.float64, device=dev)
+    if cuda_cores or _os.environ.get("MN_DEN_CUDA_CORES"):
+        q32 = torch.empty((S, ldk), dtype=torch.int32, device=dev)
+        _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), S, rc.G, None, ldk, S, inv_scale, q32)
+        if rc.M > 0:
+            _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, q32, inv_scale, addend, S, out, int(out.stride(0)))
+        return out
+    rows_pad = (S + 127) // 128 * 128
+    limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
+    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), S, rc.G, limbs, ldk, rows_pad, inv_scale, None)
     if rc.M > 0:
-        _lib.call("mn_votes_den64", a1, a0, ldk, inv64, rc.M, rc.G, q32, inv_scale, addend, S, out, int(out.stride(0)))
+        _lib.call("mn_votes_den_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, S, rc.G, out,
+                  int(out.stride(0)))
     return out
 
 

@@ -241,10 +241,15 @@ def test_votes_exact_int8_limbs(eng, m, nn, g):
     assert np.abs(a0_ @ b0_.T).max() <= 6.0 * 4096.0 * np.sqrt(g), "the digit product that is not formed is a zero-mean sum"
     # node degree in double (mn_votes_den64) and the centred ratio of the epilogue
     S = min(nn, 3)
-    den = eng.votes_den64(rc, Cd[:S], addend[:S].contiguous(), S)
+    den = eng.votes_den64(rc, Cd[:S], addend[:S].contiguous(), S, cuda_cores=True)
     den_ref = (d @ bq[:S].T).astype(np.float64) * inv_ref[:, None] / sc.T[:, :S] + addend.cpu().numpy().astype(np.float64)[None, :S]
     torch.cuda.synchronize()
     assert np.array_equal(den.cpu().numpy().T, den_ref), "node degree: exact integer dot products, scaled in double"
+    # the product path forms the same eight digit products on the int8 tensor cores (two launches, the second adds
+    # the weight-1 product into the first's doubles): equal to the last bit or two of a double
+    den_tc = eng.votes_den64(rc, Cd[:S], addend[:S].contiguous(), S)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(den_tc.cpu().numpy().T, den_ref, rtol=1e-15, atol=np.abs(den_ref).max() * 1e-15)
     col_den = eng._i32((np.arange(nn) % S).astype(np.int32))
     scale = eng.to_device(rng.uniform(0.5, 2.0, size=nn))
     rat = eng.votes_exact(rc, Cd, addend, nn, den=den, col_den=col_den, col_scale=scale)
