@@ -20,7 +20,8 @@
 
 namespace mn {
 
-constexpr int RC_WARPS = 4;
+constexpr int RC_WARPS = 14;         // warps per CTA without a stash: 14 x 8 KB of bins = 113 KB, two CTAs = 28 warps per SM
+constexpr int RC_WARPS_STASH = 4;    // with the uint16 stash of the row (CSR input, column gathers): small CTAs pack better
 constexpr int RC_HB = 2048;          // histogram bins = largest count + 1 this path handles
 constexpr int RC_INFLIGHT = 8;       // 128-bit loads in flight per lane (4 KB per warp)
 
@@ -73,7 +74,8 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
     uint32_t* tab = reinterpret_cast<uint32_t*>(smem_raw + wib * per_warp);      // histogram, then entry table
     uint16_t* vals = reinterpret_cast<uint16_t*>(tab + RC_HB);                    // the row as uint16 (STASH only)
     const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(tab);
-    const int64_t warps_total = (int64_t)gridDim.x * RC_WARPS;
+    const int cta_warps = blockDim.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * cta_warps;
     const int G4 = G >> 2;
     const int c = G + 1;
     const bool one_limb = G <= 127;
@@ -81,7 +83,7 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
     for (int b = lane; b < RC_HB; b += 32) tab[b] = 0u;
     __syncwarp();
 
-    for (int64_t row = (int64_t)blockIdx.x * RC_WARPS + wib; row < M; row += warps_total) {
+    for (int64_t row = (int64_t)blockIdx.x * cta_warps + wib; row < M; row += warps_total) {
         const int64_t src = row_index ? (int64_t)row_index[row] : row;
         const float* x = X + src * ldx;
         // ---- 1. load, histogram (and stash) -------------------------------------------------------
@@ -206,44 +208,65 @@ rank_count_kernel(const float* __restrict__ X, int64_t ldx, const int32_t* __res
         if (MODE == RC_MODE_LIMB) {
             uint32_t* p1 = reinterpret_cast<uint32_t*>(limb.a1 + row * limb.ldk);
             uint32_t* p0 = reinterpret_cast<uint32_t*>(limb.a0 + row * limb.ldk);
-            for (int g4 = lane; g4 < (int)(limb.ldk >> 2); g4 += 32) {
-                const int g = 4 * g4;
-                uint32_t e[4] = {0u, 0u, 0u, 0u};
-                if (!drop && g + 3 < G) {
-                    int v[4];
-                    quad(g, v);
+            const int n4 = (int)(limb.ldk >> 2);
+            for (int gb = 0; gb < n4; gb += 128) {
+                int v[4][4];
+                // four independent quads per lane: their loads (the L2 re-read of the row) are all in flight together
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = tab[v[u]];
-                } else if (!drop) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (g + u < G) e[u] = tab[single(g + u)];
+                for (int w = 0; w < 4; ++w) {
+                    const int g = 4 * (gb + w * 32 + lane);
+                    if (!drop && g + 3 < G) quad(g, v[w]);
                 }
-                const uint32_t r01 = e[0] | (e[1] << 16), r23 = e[2] | (e[3] << 16);
-                p1[g4] = __byte_perm(r01, r23, 0x7531);
-                p0[g4] = __byte_perm(r01, r23, 0x6420);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int g4 = gb + w * 32 + lane;
+                    const int g = 4 * g4;
+                    if (g4 >= n4) continue;
+                    uint32_t e[4] = {0u, 0u, 0u, 0u};
+                    if (!drop && g + 3 < G) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = tab[v[w][u]];
+                    } else if (!drop) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (g + u < G) e[u] = tab[single(g + u)];
+                    }
+                    const uint32_t r01 = e[0] | (e[1] << 16), r23 = e[2] | (e[3] << 16);
+                    p1[g4] = __byte_perm(r01, r23, 0x7531);
+                    p0[g4] = __byte_perm(r01, r23, 0x6420);
+                }
             }
         } else if (MODE == RC_MODE_PLANE1 || MODE == RC_MODE_PLANE2) {
             uint2* ph = reinterpret_cast<uint2*>(d_hi + row * ldd);
             uint2* pl = reinterpret_cast<uint2*>(d_lo + row * ldd);
-            for (int g4 = lane; g4 < (int)(ldd >> 2); g4 += 32) {                 // ldd is a multiple of 8
-                const int g = 4 * g4;
-                uint32_t e[4] = {0u, 0u, 0u, 0u};
-                if (!drop && g + 3 < G) {
-                    int v[4];
-                    quad(g, v);
+            const int n4 = (int)(ldd >> 2);                                       // ldd is a multiple of 8
+            for (int gb = 0; gb < n4; gb += 128) {
+                int v[4][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = tab[v[u]];
-                } else if (!drop) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (g + u < G) e[u] = tab[single(g + u)];
+                for (int w = 0; w < 4; ++w) {                                     // four quads in flight per lane
+                    const int g = 4 * (gb + w * 32 + lane);
+                    if (!drop && g + 3 < G) quad(g, v[w]);
                 }
-                if (MODE == RC_MODE_PLANE1) {
-                    ph[g4] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
-                } else {
-                    ph[g4] = make_uint2(__byte_perm(e[0], e[1], 0x5410), __byte_perm(e[2], e[3], 0x5410));
-                    pl[g4] = make_uint2(__byte_perm(e[0], e[1], 0x7632), __byte_perm(e[2], e[3], 0x7632));
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int g4 = gb + w * 32 + lane;
+                    const int g = 4 * g4;
+                    if (g4 >= n4) continue;
+                    uint32_t e[4] = {0u, 0u, 0u, 0u};
+                    if (!drop && g + 3 < G) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = tab[v[w][u]];
+                    } else if (!drop) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (g + u < G) e[u] = tab[single(g + u)];
+                    }
+                    if (MODE == RC_MODE_PLANE1) {
+                        ph[g4] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+                    } else {
+                        ph[g4] = make_uint2(__byte_perm(e[0], e[1], 0x5410), __byte_perm(e[2], e[3], 0x5410));
+                        pl[g4] = make_uint2(__byte_perm(e[0], e[1], 0x7632), __byte_perm(e[2], e[3], 0x7632));
+                    }
                 }
             }
         } else {
@@ -283,8 +306,9 @@ static int launch_mode(const float* X, int64_t ldx, const int32_t* row_index, co
                        __half* d_hi, __half* d_lo, int64_t ldd, float* inv_norm, uint8_t* flags, float* xnorm,
                        int32_t* rank2, int drop_mode, cudaStream_t st, CsrIn csr, LimbOut limb) {
     const int g_pad = (G + 7) & ~7;
+    const int cta_warps = STASH ? RC_WARPS_STASH : RC_WARPS;
     const size_t per_warp = (size_t)RC_HB * 4 + (STASH ? (size_t)g_pad * 2 : 0);
-    const size_t smem = per_warp * RC_WARPS;
+    const size_t smem = per_warp * cta_warps;
     // (set on every launch: the attribute is per device and per context, and the call costs about a microsecond)
     if (smem > 40 * 1024)
         MN_CUDA(cudaFuncSetAttribute(rank_count_kernel<MODE, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -293,11 +317,11 @@ static int launch_mode(const float* X, int64_t ldx, const int32_t* row_index, co
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // a persistent grid of exactly the resident CTAs: more would run as a second, partly filled wave
     int per_sm = 1;
-    MN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_count_kernel<MODE, STASH>, RC_WARPS * 32, smem));
-    int64_t blocks = (M + RC_WARPS - 1) / RC_WARPS;
+    MN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_count_kernel<MODE, STASH>, cta_warps * 32, smem));
+    int64_t blocks = (M + cta_warps - 1) / cta_warps;
     const int64_t max_blocks = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     if (blocks > max_blocks) blocks = max_blocks;
-    rank_count_kernel<MODE, STASH><<<(unsigned)blocks, RC_WARPS * 32, smem, st>>>(
+    rank_count_kernel<MODE, STASH><<<(unsigned)blocks, cta_warps * 32, smem, st>>>(
         X, ldx, row_index, col_index, M, G, g_pad, d_hi, d_lo, ldd, inv_norm, flags, xnorm, rank2, drop_mode, csr, limb);
     MN_LAUNCH_CHECK();
     return 0;
