@@ -944,7 +944,11 @@ SHARD_UPLOAD = _os.environ.get("MN_SHARD_UPLOAD", "1") != "0"     # multi-GPU: e
 STREAM_MIN_BYTES = 64 << 20
 STREAM_EARLY_BYTES = 400 << 20          # queued before the host encodes labels (~8 ms of PCIe Gen5)
 STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "16"))
-STREAM_DEV_CHUNKS = int(_os.environ.get("MN_STREAM_DEV_CHUNKS", "4"))     # row chunks of the passes; 0 = as many as uploads
+# row chunks of the passes (0 = as many as uploads).  Every chunk costs ~0.6 ms of launch tails, but the LAST one -- the
+# first rows against all columns, the largest -- can only start when the whole matrix has arrived: on boxes whose
+# H2D link runs at ~27 GB/s instead of ~55 that wait dominates.  Modelled / measured end-to-end times at config 2:
+# 55 GB/s: 4 chunks 108.0 ms, 6: 107.6, 8: 108.8;  27 GB/s: 124.1 / 120.3 / 118.8.  6 is neutral on the fast link.
+STREAM_DEV_CHUNKS = int(_os.environ.get("MN_STREAM_DEV_CHUNKS", "6"))
 
 
 def start_upload(X, full_network: bool = False):
