@@ -330,6 +330,13 @@ int mn_one_vs_best(const float* votes, int64_t ldv, int32_t ncols, const float* 
                    const int32_t* lab_row_off, const int32_t* cell_label, int32_t n_labels,
                    const double* auroc, double* out, mn_stream_t stream);
 
+/* Multi-GPU centroid paths: after the all-to-all of the votes, rank r holds its train columns for the
+ * cells of all ranks as [chunk][source rank][column][cell in chunk]; this puts them into [column, global device row]
+ * order for K6 / K7: out[c, p] = recv[cell_off[p] + c * col_stride] (cell_off: int64 [N], built by the host from
+ * the cell shard bookkeeping). */
+int mn_votes_unpack(const float* recv, const int64_t* cell_off, int64_t N, int32_t n_cols, int64_t col_stride,
+                    float* out, int64_t ldo, mn_stream_t stream);
+
 /* ---- supervised MetaNeighbor, fast_version: all gene sets of one rank in one call --------------------------
  * Replaces the per-gene-set loop of MetaNeighbor.py:84-93 over score_low_mem (:106-148) / compute_votes (:151-176):
  * for each set j (gene columns all_cols[set_off[j] .. set_off[j+1]) of X, at most g_max of them) the host loop --

@@ -50,6 +50,7 @@ SIGNATURES = {
     "mn_votes_finalize": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "mn_mask_dropped": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "mn_loso_finalize": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "mn_votes_unpack": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),
     "mn_supervised_fast_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "mn_supervised_fast_sets": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
                                           _i64, _vp, _i64, _vp, _vp, _vp]),

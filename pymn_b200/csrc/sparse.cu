@@ -25,7 +25,27 @@ __global__ void csc_gather_kernel(const int64_t* __restrict__ indptr, const int3
     }
 }
 
+// out[c, p] = recv[cell_off[p] + c * col_stride]: the received vote chunks of the cell-sharded centroid path
+// ([chunk][source rank][column][cell in chunk]) -> [column, global device row] in one pass
+__global__ void votes_unpack_kernel(const float* __restrict__ recv, const int64_t* __restrict__ cell_off, int64_t N,
+                                    int64_t col_stride, float* __restrict__ out, int64_t ldo) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int c = blockIdx.y;
+    out[(int64_t)c * ldo + p] = recv[cell_off[p] + (int64_t)c * col_stride];
+}
+
 }  // namespace mn
+
+extern "C" int mn_votes_unpack(const float* recv, const int64_t* cell_off, int64_t N, int32_t n_cols, int64_t col_stride,
+                               float* out, int64_t ldo, mn_stream_t stream) {
+    MN_CHECK_ARG(recv && cell_off && out && N >= 1 && n_cols >= 1 && n_cols <= 65535 && ldo >= N,
+                 "mn_votes_unpack: bad arguments");
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)n_cols);
+    mn::votes_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(recv, cell_off, N, col_stride, out, ldo);
+    MN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int mn_csc_gather_dense(const int64_t* indptr, const int32_t* indices, const float* data,
                                    const int32_t* cols, int32_t col0, int32_t n_cols, int64_t N, float* out, int64_t ld,

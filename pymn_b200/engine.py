@@ -336,6 +336,32 @@ def cell_limbs(rc: RankedCells):
     return rc._limbs
 
 
+def centroid_limbs(rc: RankedCells, C: torch.Tensor, Nn: int):
+    """The Nn centroid rows of C as four stacked int8 digit planes: (limbs [4 * rows_pad, ldk], rows_pad, inv_scale [Nn])."""
+    dev = rc.device
+    ldk = cell_limbs(rc)[2]
+    rows_pad = (Nn + 127) // 128 * 128
+    limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
+    inv_scale = torch.empty((Nn,), dtype=torch.float32, device=dev)
+    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale, None)
+    return limbs, rows_pad, inv_scale
+
+
+def votes_exact_launch(rc: RankedCells, cl, addend, Nn: int, out: torch.Tensor, r0: int = 0, r1: int = None, den=None,
+                       col_den=None, col_scale=None):
+    """One launch of the exact vote GEMM for the cells [r0, r1) of ``rc`` against the centroid digits ``cl``
+    (centroid_limbs): column-major votes into ``out`` [Nn, ldo >= r1 - r0] (float32, or float64 = the raw values)."""
+    a1, a0, ldk, inv64 = cell_limbs(rc)
+    r1 = rc.M if r1 is None else int(r1)
+    if r1 <= r0:
+        return
+    limbs, rows_pad, inv_scale = cl
+    as_double = out.dtype == torch.float64
+    _lib.call("mn_votes_fast_i8", a1[r0:r1], a0[r0:r1], ldk, inv64[r0:r1], r1 - r0, limbs, ldk, rows_pad, inv_scale, addend,
+              Nn, rc.G, None if as_double else out, out if as_double else None, int(out.stride(0)),
+              den[:, r0:r1] if den is not None else None, int(den.stride(0)) if den is not None else 0, col_den, col_scale)
+
+
 def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col_den=None, col_scale=None,
                 as_double=False, ldo: int = 0):
     """K3, exact form (the product path): votes of all cells for the Nn centroid rows of C (float32 [>= Nn, ld])
@@ -343,18 +369,10 @@ def votes_exact(rc: RankedCells, C: torch.Tensor, addend, Nn: int, den=None, col
     val = x.c + addend;  with ``den`` (double [S, M]) val = val / den[col_den[n]] * col_scale[n] - 1, otherwise
     val -= col_scale[n].  Returns [Nn, max(M, ldo)] column-major, float32 (rounded once) or float64 (``as_double``)."""
     dev = rc.device
-    a1, a0, ldk, inv64 = cell_limbs(rc)
-    rows_pad = (Nn + 127) // 128 * 128
-    limbs = torch.zeros((4 * rows_pad, ldk), dtype=torch.int8, device=dev)
-    inv_scale = torch.empty((Nn,), dtype=torch.float32, device=dev)
-    _lib.call("mn_limb_split_centroids", C, int(C.stride(0)), Nn, rc.G, limbs, ldk, rows_pad, inv_scale, None)
-    ldo = max(int(ldo), rc.M)          # (a pitch > M leaves zeroed padding: equal blocks for the votes exchange)
+    ldo = max(int(ldo), rc.M)          # (a pitch > M leaves zeroed padding)
     out = (torch.zeros if ldo > rc.M else torch.empty)((Nn, ldo), dtype=torch.float64 if as_double else torch.float32,
                                                        device=dev)
-    if rc.M > 0:
-        _lib.call("mn_votes_fast_i8", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, addend, Nn, rc.G,
-                  None if as_double else out, out if as_double else None, ldo,
-                  den, int(den.stride(0)) if den is not None else 0, col_den, col_scale)
+    votes_exact_launch(rc, centroid_limbs(rc, C, Nn), addend, Nn, out, 0, rc.M, den, col_den, col_scale)
     return out
 
 
@@ -548,7 +566,9 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
     # (rounding numerator and denominator to float32 first costs 3-4 rank flips per AUROC cell at 5,000 cells
     # per study).
     n_b = n_train + (n_train_studies if ndn else 0)
+    if t: t.start("votes_ref")
     mu = _column_reference(Xd, base, sh, C, n_b)
+    if t: t.stop("votes_ref")
     if world > 1:
         # columns in destination order: rank d's columns d, d + world, ... as one block of n_max rows (padding
         # rows repeat column 0 and are dropped after the exchange)
@@ -561,20 +581,40 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
         order = None
     pick = (lambda v: v.index_select(0, order).contiguous()) if order is not None else (lambda v: v[:n_train].contiguous())
     n_cols = world * n_max if world > 1 else n_train
-    ldo = sh.per if world > 1 else 0
     if ndn:
         addend = n_valid[:n_b].contiguous()
         num_ref = mu[:n_train] + addend[:n_train].double()
         den_ref = (mu[n_train:] + addend[n_train:].double()).index_select(0, train_study.long())
         ref = num_ref / den_ref
         scale = torch.where(torch.isfinite(ref) & (ref > 0), 1.0 / ref, torch.ones_like(ref))
+        if t: t.start("votes_den")
         den64 = votes_den64(rc, C[n_train:n_b], addend[n_train:n_b].contiguous(), n_train_studies)
-        out = votes_exact(rc, pick(C), pick(addend), n_cols, den=den64, col_den=pick(train_study),
-                          col_scale=pick(scale), ldo=ldo)
+        if t: t.stop("votes_den")
+        kw = dict(den=den64, col_den=pick(train_study), col_scale=pick(scale))
+        add_cols = pick(addend)
     else:
-        out = votes_exact(rc, pick(C), None, n_cols, col_scale=pick(mu), ldo=ldo)
-    if world > 1:
-        out = exchange_votes(out, sh, n_max, gidx)
+        kw = dict(col_scale=pick(mu))
+        add_cols = None
+    cl = centroid_limbs(rc, pick(C), n_cols)
+    if world == 1:
+        out = torch.empty((n_cols, rc.M), dtype=torch.float32, device=dev)
+        votes_exact_launch(rc, cl, add_cols, n_cols, out, 0, rc.M, **kw)
+    else:
+        # The own cells go through the GEMM in Q row chunks; the all-to-all of chunk q runs (on NCCL's stream) while
+        # the tensor cores work on chunk q + 1, so only the last chunk's exchange is exposed.
+        Q = votes_chunks(sh.per)
+        clen = ((sh.per + Q - 1) // Q + 127) // 128 * 128
+        send = torch.zeros((Q, n_cols, clen), dtype=torch.float32, device=dev)
+        for q in range(Q):
+            votes_exact_launch(rc, cl, add_cols, n_cols, send[q], q * clen, min(rc.M, (q + 1) * clen), **kw)
+            if q == 0:
+                recv, works = exchange_votes_begin(send, q)
+            else:
+                exchange_votes_begin(send, q, recv, works)
+        if t: t.start("votes_exchange_tail")
+        out = exchange_votes_end(recv, works, sh, n_max, gidx)
+        if t: t.stop("votes_exchange_tail")
+        del send
     if t: t.stop("votes_gemm")
     if n_loc > 0:
         if t: t.start("auroc")
@@ -595,17 +635,52 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
             _allreduce_max(n_pos), flags)
 
 
-def exchange_votes(out: torch.Tensor, sh: CellShard, n_max: int, gidx: torch.Tensor) -> torch.Tensor:
-    """The votes exchange of the cell-sharded centroid path: ``out`` [world * n_max, per] holds the votes of this
-    rank's cells (local order, zero-padded to ``per``) for ALL train columns, destination rank d's columns in rows
-    [d * n_max, (d + 1) * n_max).  One all-to-all hands every rank its own columns for the cells of all ranks;
-    returns [n_max, N] with the cells in global device row order."""
+VOTES_CHUNKS = int(_os.environ.get("MN_VOTES_CHUNKS", "8"))
+
+
+def votes_chunks(per: int) -> int:
+    """Row chunks of the cell-sharded vote GEMM (each followed by its own all-to-all): 8 when the chunks stay large
+    (only the last chunk's exchange is exposed: NCCL's all-to-all moves ~110 GB/s per rank here)."""
+    return max(1, min(VOTES_CHUNKS, per // 4096))
+
+
+def exchange_votes_begin(send: torch.Tensor, q: int, recv: torch.Tensor = None, works: list = None):
+    """Start the all-to-all of row chunk q.  ``send`` [Q, world * n_max, clen]: votes of this rank's cells (local order,
+    chunk q = cells [q clen, (q + 1) clen), zero-padded) for ALL train columns, destination rank d's columns in rows
+    [d n_max, (d + 1) n_max).  Asynchronous: the collective waits for the work queued on the current stream (the
+    GEMM of this chunk) and runs on the process group's own stream.  Returns (recv, works)."""
     import torch.distributed as dist
-    world = sh.world
-    recv = torch.empty_like(out)
-    dist.all_to_all_single(recv.view(-1), out.view(-1))
-    # [source rank, column, local cell] -> [column, global device row]
-    return recv.view(world, n_max, sh.per).permute(1, 0, 2).reshape(n_max, world * sh.per).index_select(1, gidx)
+    if recv is None:
+        recv, works = torch.empty_like(send), []
+    works.append(dist.all_to_all_single(recv[q].view(-1), send[q].view(-1), async_op=True))
+    return recv, works
+
+
+def exchange_votes_end(recv: torch.Tensor, works: list, sh: CellShard, n_max: int, gidx: torch.Tensor) -> torch.Tensor:
+    """Wait for the chunk exchanges and put the cells into global device row order: [n_max, N] (this rank's train
+    columns for the cells of all ranks).  ``gidx`` addresses rank-major blocks of ``sh.per`` cells; the chunked
+    buffers hold blocks of Q * clen >= per cells per rank."""
+    for w in works:
+        w.wait()
+    Q, clen, world = int(recv.shape[0]), int(recv.shape[2]), sh.world
+    per_pad = Q * clen
+    if recv.is_cuda:
+        # one pass: cell p sits at chunk q, source rank src, position i -> offset ((q world + src) n_max) clen + i
+        src, lpos = gidx // sh.per, gidx % sh.per
+        off = ((lpos // clen) * world + src) * (n_max * clen) + lpos % clen
+        out = torch.empty((n_max, sh.N), dtype=recv.dtype, device=recv.device)
+        _lib.call("mn_votes_unpack", recv, off, sh.N, n_max, clen, out, sh.N)
+        return out
+    # (host tensors -- the gloo tests of this bookkeeping -- take the same route with torch index operations)
+    gv = (gidx // sh.per) * per_pad + gidx % sh.per if per_pad != sh.per else gidx
+    # [chunk, source rank, column, cell in chunk] -> [column, source rank, chunk, cell in chunk] = [column, padded cell]
+    return recv.view(Q, world, n_max, clen).permute(2, 1, 0, 3).reshape(n_max, world * per_pad).index_select(1, gv)
+
+
+def exchange_votes(out: torch.Tensor, sh: CellShard, n_max: int, gidx: torch.Tensor) -> torch.Tensor:
+    """The votes exchange of the cell-sharded centroid path in one piece: ``out`` [world * n_max, per] -> [n_max, N]."""
+    recv, works = exchange_votes_begin(out.unsqueeze(0), 0)
+    return exchange_votes_end(recv, works, sh, n_max, gidx)
 
 
 def _gather_columns(local: torch.Tensor, n_total: int, rank: int, world: int) -> torch.Tensor:

@@ -116,6 +116,21 @@ def _worker_cells(rank, world, port, seed, out_dir):
         mine = engine.exchange_votes(out, sh, n_max, gidx)
         for k, col in enumerate(range(rank, n_train, world)):
             assert np.array_equal(mine[k].numpy(), 1000.0 * col + lay.perm.astype(np.float32)), (rank, col)
+        # the same in two row chunks, each with its own (asynchronous) all-to-all, blocks padded beyond `per`
+        Q = 2
+        clen = (sh.per + Q - 1) // Q + 3
+        send = torch.zeros((Q, world * n_max, clen), dtype=torch.float32)
+        for q in range(Q):
+            own = sh.rows[q * clen:(q + 1) * clen].astype(np.float32)
+            for d in range(world):
+                for k, col in enumerate(range(d, n_train, world)):
+                    send[q, d * n_max + k, :len(own)] = torch.from_numpy(1000.0 * col + own)
+            if q == 0:
+                recv, works = engine.exchange_votes_begin(send, q)
+            else:
+                engine.exchange_votes_begin(send, q, recv, works)
+        mine2 = engine.exchange_votes_end(recv, works, sh, n_max, gidx)
+        assert torch.equal(mine2[:len(range(rank, n_train, world))], mine[:len(range(rank, n_train, world))])
         np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.ones(1))
     finally:
         dist.destroy_process_group()
