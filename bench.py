@@ -659,6 +659,8 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        engine.release_peer_buffers()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -206,6 +206,19 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
                      const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
                      const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
                      mn_stream_t stream);
+/* mn_votes_fast_i8 fused with the votes exchange of the multi-GPU centroid paths: the Nn = world *
+ * cols_per_rank train columns are arranged by owner (rank d owns columns [d cols_per_rank, (d + 1) cols_per_rank)),
+ * and the epilogue stores the votes of this rank's M cells for column n straight into the OWNER's receive buffer --
+ * a peer pointer, written over NVLink tile by tile while the tensor cores work on the next tiles -- at
+ * peer_out[d][(src_rank * cols_per_rank + n % cols_per_rank) * per + m].  peer_out_host: HOST array of `world`
+ * device pointers (float32 [world * cols_per_rank, per] each, mapped into this process: CUDA IPC / peer access are
+ * the caller's business); per >= M.  No NCCL collective moves the votes; the caller fences the ranks before the
+ * launch (the receive buffers are free) and after it (all writes have landed). */
+int mn_votes_fast_i8_peer(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                          const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
+                          const float* addend, int32_t Nn, int32_t G, float* const* peer_out_host, int32_t world,
+                          int32_t src_rank, int32_t cols_per_rank, int64_t per, const double* den, int64_t ld_den,
+                          const int32_t* col_den, const double* col_scale, mn_stream_t stream);
 /* Node degree on the int8 tensor cores, FULLY exact: den[s, m] = inv_norm64[m] * inv_scale[s] * sum_g d[m, g] q[s, g]
  * + addend[s] for the S study-centroid rows whose limbs are b_limbs (mn_limb_split_centroids): the seven digit
  * products of mn_votes_fast_i8 plus, in a second launch that adds into `out`, the weight-1 product a0 * b0 that the

@@ -42,6 +42,8 @@ SIGNATURES = {
     "mn_votes_den64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "mn_votes_fast_i8": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i64,
                                    _vp, _i64, _vp, _vp, _vp]),
+    "mn_votes_fast_i8_peer": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32,
+                                        _i64, _vp, _i64, _vp, _vp, _vp]),
     "mn_votes_den_i8": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "mn_corr_hist": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mn_corr_spill_layout": (C.c_int, [_i64, _i64, _i64, _i32, _i32, _i32, C.POINTER(_i64), C.POINTER(_i64)]),

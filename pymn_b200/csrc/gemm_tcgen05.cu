@@ -67,6 +67,13 @@ struct GemmParams {
     int cls_mul;                  // weight of accumulator slot 0 (128 with two limbs of A, 1 with one)
     int n_cls;                    // accumulator slots in use (4; 1 for the lone a0 * b0 product of mn_votes_den_i8)
     int acc64;                    // 1: out64 += val instead of out64 = val
+    // peer mode (multi-GPU centroid paths, mn_votes_fast_i8_peer): column n belongs to rank n / peer_cols and is
+    // stored straight into THAT rank's receive buffer over NVLink, at [peer_src][n % peer_cols][m] (pitch peer_per)
+    float* peer_out[8];
+    int peer_world;               // 0 = off
+    int peer_src;
+    int peer_cols;
+    int64_t peer_per;
     const double* inv_a64;        // [M] exact-ish row scale 1/||d|| (double)
     // ... its epilogue, all in double:  val = dot * inv_a64[m] * inv_b[n] + addend[n];
     //   den != null:  val = val / den[col_den[n] * ld_den + m] * col_scale[n] - 1     (node-degree ratio, centred)
@@ -571,6 +578,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
     // elements of one k-block along the TMA's K coordinate: 128 bytes either way (64 fp16 / 128 int8)
     constexpr int BKE = I8 ? 128 : BK;
     static_assert(!I8 || (EPI == EPI_STORE && NCHAIN == 4), "the int8 form is wired for the vote store epilogue");
+    static_assert(!I8 || (EW * (BN / 2) * 4 >= BN * 16), "int8 epilogue keeps a double and a pointer per column in s_colw");
     static_assert(CTAS == 1 || CTAS == 2 || CTAS == 4, "1 CTA, a pair, or two pairs");
     constexpr int B_ROWS = BN / (PAIR ? 2 : 1);    // rows of the B tile this CTA stages
     constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -914,6 +922,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                 if (EPI == EPI_STORE && I8) {
                     s_lab[c] = (ok && p.den) ? p.col_den[n] : 0;
                     reinterpret_cast<double*>(s_colw)[c] = (ok && p.col_scale) ? p.col_scale[n] : (p.den ? 1.0 : 0.0);
+                    // where this column's votes go: the local column-major matrix, or (peer mode) the receive buffer of
+                    // the rank that owns the column -- a peer pointer, written over NVLink by the stores below
+                    float* dst = nullptr;
+                    if (ok && p.out) {
+                        dst = p.out + n * p.ldo;
+                        if (p.peer_world > 0) {
+                            const int d = (int)(n / p.peer_cols);
+                            dst = p.peer_out[d] + ((int64_t)p.peer_src * p.peer_cols + (n - (int64_t)d * p.peer_cols)) * p.peer_per;
+                        }
+                    }
+                    reinterpret_cast<float**>(reinterpret_cast<double*>(s_colw) + BN)[c] = dst;
                 }
                 if (EPI == EPI_VOTE) {
                     const int lab = ok ? p.label[n] : 0;
@@ -959,6 +978,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                     for (int c = 0; c < 32; ++c) v[c] *= p.cls_mul;
                     if (row_ok) {
                         const double* s_scale64 = reinterpret_cast<const double*>(s_colw);
+                        float* const* s_dst = reinterpret_cast<float* const*>(s_scale64 + BN);
                         int last_sd = -1;
                         double rden = 1.0;
 #pragma unroll
@@ -979,7 +999,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__
                                     val -= s_scale64[c0 + c];
                                 }
                                 if (p.out64) p.out64[n * p.ldo + m] = p.acc64 ? p.out64[n * p.ldo + m] + val : val;
-                                else p.out[n * p.ldo + m] = (float)val;
+                                else s_dst[c0 + c][m] = (float)val;
                             }
                         }
                     }
@@ -1606,7 +1626,13 @@ int mn_votes_fast(const mn_half_t* a_hi, const mn_half_t* a_lo, int64_t lda, con
     return launch_gemm<128, EPI_STORE, 4>(ah, al, lda, M, bh, bl, ldb, Nn, G, p, st);
 }
 
-static int votes_i8(int low_only, const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+struct PeerOut {
+    float* const* ptrs;     // host array of `world` device pointers (receive buffers), nullptr = off
+    int world, src, cols;
+    int64_t per;
+};
+
+static int votes_i8(int low_only, PeerOut peer, const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
                      const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
                      const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
                      const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
@@ -1666,6 +1692,19 @@ static int votes_i8(int low_only, const int8_t* a1, const int8_t* a0, int64_t ld
         const int v = atoi(e);
         if (v == 1 || v == 2) ctas = v;
     }
+    if (peer.ptrs) {
+        MN_CHECK_ARG(peer.world >= 2 && peer.world <= 8 && peer.src >= 0 && peer.src < peer.world && peer.cols >= 1 &&
+                         peer.per >= M && Nn <= peer.world * peer.cols && out && !out64,
+                     "mn_votes_fast_i8_peer: bad peer layout");
+        for (int r = 0; r < peer.world; ++r) {
+            MN_CHECK_ARG(peer.ptrs[r] != nullptr, "mn_votes_fast_i8_peer: null receive buffer of rank %d", r);
+            p.peer_out[r] = peer.ptrs[r];
+        }
+        p.peer_world = peer.world;
+        p.peer_src = peer.src;
+        p.peer_cols = peer.cols;
+        p.peer_per = peer.per;
+    }
     p.b_limb_rows = b_limb_rows;
     p.tri = 0;
     p.mt0 = 0;
@@ -1691,18 +1730,30 @@ int mn_votes_fast_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const doub
                      const float* addend, int32_t Nn, int32_t G, float* out, double* out64, int64_t ldo,
                      const double* den, int64_t ld_den, const int32_t* col_den, const double* col_scale,
                      mn_stream_t stream) {
-    return votes_i8(0, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, addend, Nn, G, out, out64, ldo, den,
-                    ld_den, col_den, col_scale, stream);
+    return votes_i8(0, PeerOut{nullptr, 0, 0, 0, 0}, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, addend, Nn,
+                    G, out, out64, ldo, den, ld_den, col_den, col_scale, stream);
+}
+
+int mn_votes_fast_i8_peer(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
+                          const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale,
+                          const float* addend, int32_t Nn, int32_t G, float* const* peer_out_host, int32_t world,
+                          int32_t src_rank, int32_t cols_per_rank, int64_t per, const double* den, int64_t ld_den,
+                          const int32_t* col_den, const double* col_scale, mn_stream_t stream) {
+    MN_CHECK_ARG(peer_out_host != nullptr, "mn_votes_fast_i8_peer: null pointer table");
+    return votes_i8(0, PeerOut{peer_out_host, world, src_rank, cols_per_rank, per}, a1, a0, lda, inv_norm64, M, b_limbs, ldb,
+                    b_limb_rows, inv_scale, addend, Nn, G, peer_out_host[src_rank], nullptr, per, den, ld_den, col_den,
+                    col_scale, stream);
 }
 
 int mn_votes_den_i8(const int8_t* a1, const int8_t* a0, int64_t lda, const double* inv_norm64, int64_t M,
                     const int8_t* b_limbs, int64_t ldb, int32_t b_limb_rows, const float* inv_scale, const float* addend,
                     int32_t S, int32_t G, double* out, int64_t ldo, mn_stream_t stream) {
     MN_CHECK_ARG(out != nullptr, "mn_votes_den_i8: null output");
-    int rc = votes_i8(0, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, addend, S, G, nullptr, out, ldo,
+    const PeerOut none{nullptr, 0, 0, 0, 0};
+    int rc = votes_i8(0, none, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, addend, S, G, nullptr, out, ldo,
                       nullptr, 0, nullptr, nullptr, stream);
     if (rc || G <= 127) return rc;          // one digit per rank: the four products above are the whole dot product
-    return votes_i8(1, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, nullptr, S, G, nullptr, out, ldo,
+    return votes_i8(1, none, a1, a0, lda, inv_norm64, M, b_limbs, ldb, b_limb_rows, inv_scale, nullptr, S, G, nullptr, out, ldo,
                     nullptr, 0, nullptr, nullptr, stream);
 }
 

@@ -464,8 +464,25 @@ class CellShard:
     max_label_rows: int
     gidx: np.ndarray
 
+    def on_device(self, name: str, make):
+        """Device copy of a host array derived from this shard, uploaded once per device (the bench and repeated API
+        calls on one layout reuse it)."""
+        cache = self.__dict__.setdefault("_dev", {})
+        key = (name, torch.cuda.current_device())
+        if key not in cache:
+            cache[key] = make()
+        return cache[key]
+
 
 def cell_shard(lay: LabelLayout, rank: int, world: int) -> CellShard:
+    """The cell shard of (rank, world) for a layout, computed once per layout (a few O(N) host passes)."""
+    cache = lay.__dict__.setdefault("_shards", {})
+    if (rank, world) not in cache:
+        cache[(rank, world)] = _cell_shard(lay, rank, world)
+    return cache[(rank, world)]
+
+
+def _cell_shard(lay: LabelLayout, rank: int, world: int) -> CellShard:
     perm = np.asarray(lay.perm)
     N, L = int(perm.shape[0]), len(lay.row_labels)
     if world == 1:
@@ -482,6 +499,21 @@ def cell_shard(lay: LabelLayout, rank: int, world: int) -> CellShard:
         lpos[idx] = np.arange(idx.shape[0])
     return CellShard(rank, world, N, per, lo, hi, perm[mine], np.concatenate([[0], np.cumsum(counts)]).astype(np.int32),
                      int(counts.max()) if L else 0, src.astype(np.int64) * per + lpos)
+
+
+def lay_dev(lay: LabelLayout, name: str) -> torch.Tensor:
+    """int32 device copy of one of the layout's index arrays, uploaded once per layout and device."""
+    cache = lay.__dict__.setdefault("_dev", {})
+    key = (name, torch.cuda.current_device())
+    if key not in cache:
+        cache[key] = _i32(getattr(lay, name))
+    return cache[key]
+
+
+def ctypes_addr(arr) -> int:
+    """Address of a ctypes array (a host pointer argument of the C ABI)."""
+    import ctypes
+    return ctypes.addressof(arr)
 
 
 def _gather_cells(local: torch.Tensor, sh: CellShard, gidx: torch.Tensor) -> torch.Tensor:
@@ -509,7 +541,8 @@ def _device_matrix(X):
 
 def local_ranked_cells(Xd, base: int, sh: CellShard, drop_mode=0):
     """K1 over this rank's cells in local label-sorted order (``Xd`` row 0 = input row ``base``)."""
-    return rank_normalize(Xd, row_index=_i32(sh.rows - base), drop_mode=drop_mode, limbs=True)
+    rows = sh.on_device(f"rows-{base}", lambda: _i32(sh.rows - base))
+    return rank_normalize(Xd, row_index=rows, drop_mode=drop_mode, limbs=True)
 
 
 def _column_reference(Xd, base: int, sh: CellShard, C: torch.Tensor, n_rows: int) -> torch.Tensor:
@@ -556,10 +589,10 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
     t = timer
     n_max = (n_train + world - 1) // world
     n_loc = len(range(rank, n_train, world))
-    gidx = to_device(sh.gidx) if world > 1 else None
+    gidx = sh.on_device("gidx", lambda: to_device(sh.gidx)) if world > 1 else None
     flags = _gather_cells(rc.flags, sh, gidx)
-    cell_label = mask_dropped(_i32(lay.cell_label), _gather_cells(rc.inv_norm, sh, gidx))
-    seg_off = _i32(lay.seg_off)
+    cell_label = mask_dropped(lay_dev(lay, "cell_label"), _gather_cells(rc.inv_norm, sh, gidx))
+    seg_off = lay_dev(lay, "seg_off")
     if t: t.start("votes_gemm")
     # Exact integer dot products; the node-degree ratio is taken in double inside the epilogue and centred on a
     # per-column reference so that its one float32 rounding resolves ~1e-9 of the ratio where the cells crowd
@@ -596,9 +629,29 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
         kw = dict(col_scale=pick(mu))
         add_cols = None
     cl = centroid_limbs(rc, pick(C), n_cols)
+    peer = peer_receive_buffers(n_cols * sh.per * 4, dev, rank, world) if (world > 1 and VOTES_P2P and world <= 8) else None
     if world == 1:
         out = torch.empty((n_cols, rc.M), dtype=torch.float32, device=dev)
         votes_exact_launch(rc, cl, add_cols, n_cols, out, 0, rc.M, **kw)
+    elif peer is not None:
+        # GEMM fused with the exchange: the epilogue stores every column's votes straight into its owner's receive
+        # buffer over NVLink (mn_votes_fast_i8_peer) -- no collective moves the votes.  Two tiny all-reduces fence
+        # the ranks: before the launch (everybody has finished reading its buffer from the previous call), after it
+        # (all stores have landed).
+        recv, table = peer
+        fence = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _all_reduce_sum(fence)
+        a1, a0, ldk, inv64 = cell_limbs(rc)
+        limbs, rows_pad, inv_scale = cl
+        if rc.M > 0:
+            den = kw.get("den")
+            _lib.call("mn_votes_fast_i8_peer", a1, a0, ldk, inv64, rc.M, limbs, ldk, rows_pad, inv_scale, add_cols, n_cols,
+                      rc.G, ctypes_addr(table), world, rank, n_max, sh.per, den, int(den.stride(0)) if den is not None else 0,
+                      kw.get("col_den"), kw.get("col_scale"))
+        _all_reduce_sum(fence)
+        if t: t.start("votes_exchange_tail")
+        out = exchange_votes_end(recv[:world * n_max * sh.per].view(1, world * n_max, sh.per), [], sh, n_max, gidx)
+        if t: t.stop("votes_exchange_tail")
     else:
         # The own cells go through the GEMM in Q row chunks; the all-to-all of chunk q runs (on NCCL's stream) while
         # the tensor cores work on chunk q + 1, so only the last chunk's exchange is exposed.
@@ -623,7 +676,7 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
         res = auc
         if ovb:
             if t: t.start("one_vs_best")
-            res = one_vs_best(out, n_loc, None, None, _i32(lay.seg_lab_off), n_seg, _i32(lay.lab_row_off),
+            res = one_vs_best(out, n_loc, None, None, lay_dev(lay, "seg_lab_off"), n_seg, lay_dev(lay, "lab_row_off"),
                               cell_label, n_lab, auc)
             if t: t.stop("one_vs_best")
     else:
@@ -635,6 +688,76 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
             _allreduce_max(n_pos), flags)
 
 
+# ---- peer receive buffers of the fused vote GEMM + exchange (mn_votes_fast_i8_peer) ---------------------------------
+VOTES_P2P = _os.environ.get("MN_VOTES_P2P", "1") != "0"
+_PEER = {}          # device index -> dict(nbytes, local uint8 tensor, peers [uint8 tensors of every rank], table)
+
+
+def peer_receive_buffers(nbytes: int, dev, rank: int, world: int):
+    """A receive buffer of >= nbytes on every rank, each mapped into every other rank's address space (CUDA IPC through
+    torch's storage sharing; one process per GPU on one node, NVLink / NVSwitch peer access).  Returns (local float32
+    view, host array of the `world` device pointers) or None when the mapping cannot be set up (the caller falls
+    back to NCCL's all-to-all).  Collective: every rank must call it with the same nbytes.  The buffers are cached
+    for the life of the process and only ever grow."""
+    import ctypes
+    import torch.distributed as dist
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ent = _PEER.get(idx)
+    if ent is not None and ent.get("failed"):
+        return None
+    if ent is None or ent["nbytes"] < nbytes:
+        try:
+            size = max(int(nbytes), 1 << 20)
+            size = (size + (64 << 20) - 1) // (64 << 20) * (64 << 20)          # grow in 64 MB steps
+            local = torch.empty((size,), dtype=torch.uint8, device=dev)
+            info = local.untyped_storage()._share_cuda_()
+            infos = [None] * world
+            dist.all_gather_object(infos, (rank, info))
+            peers = []
+            for r in range(world):
+                if r == rank:
+                    peers.append(local)
+                    continue
+                # opened with THIS rank's device current (not the exporter's, which torch's tensor sharing would use):
+                # cudaIpcOpenMemHandle maps the memory into the current device's address space and enables peer
+                # access lazily -- what a kernel of this device needs in order to store into it (as NCCL does)
+                info_r = (idx,) + tuple(infos[r][1][1:])
+                st = torch.UntypedStorage._new_shared_cuda(*info_r)
+                t = torch.empty((0,), dtype=torch.uint8, device=dev)
+                t.set_(st, 0, (size,), (1,))
+                peers.append(t)
+            # touching every peer once through torch enables peer access between the two devices for this context
+            probe = torch.zeros((16,), dtype=torch.uint8, device=dev)
+            for r in range(world):
+                if r != rank:
+                    probe.copy_(peers[r][:16])
+            torch.cuda.synchronize()
+            ok = torch.ones((1,), dtype=torch.int32, device=dev)
+        except Exception as e:                                 # noqa: BLE001 -- any failure = no peer path on this box
+            ok = torch.zeros((1,), dtype=torch.int32, device=dev)
+            peers, local, size = None, None, 0
+            _PEER_ERR["last"] = f"{type(e).__name__}: {e}"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)              # all ranks take the same path
+        if int(ok.item()) == 0:
+            _PEER[idx] = {"failed": True}
+            return None
+        table = (ctypes.c_void_p * world)(*[int(p.data_ptr()) for p in peers])
+        ent = _PEER[idx] = dict(nbytes=size, local=local, peers=peers, table=table)
+    n32 = ent["nbytes"] // 4
+    return ent["local"].view(torch.float32)[:n32], ent["table"]
+
+
+_PEER_ERR = {}
+
+
+def release_peer_buffers():
+    """Drop the peer mappings and the local receive buffer (collective in spirit: call it on every rank before the
+    process group goes away, so that no rank exits while another still maps its buffer)."""
+    for ent in _PEER.values():
+        ent.pop("peers", None)
+        ent.pop("local", None)
+    _PEER.clear()
+    torch.cuda.empty_cache()
 VOTES_CHUNKS = int(_os.environ.get("MN_VOTES_CHUNKS", "8"))
 
 
@@ -720,7 +843,7 @@ def _host_tables(res, auc, n_pos, flags):
 
 def _label_centroids(rc: RankedCells, sh: CellShard, L: int, extra_rows: int = 0):
     """Fixed-point label centroids over the cells of ALL ranks: local partial sums + one integer all-reduce."""
-    Cq, nq = centroids_fixed(rc, _i32(sh.lab_row_off), L, extra_rows, sh.max_label_rows)
+    Cq, nq = centroids_fixed(rc, sh.on_device("lab_row_off", lambda: _i32(sh.lab_row_off)), L, extra_rows, sh.max_label_rows)
     if sh.world > 1:
         _all_reduce_sum(Cq, nq)
     return Cq, nq
@@ -739,7 +862,7 @@ def us_fast_device(X, lay: LabelLayout, ndn=True, ovb=False, timer=None):
     L, S = len(lay.row_labels), len(lay.studies)
     if t: t.start("centroids")
     Cq, nq = _label_centroids(rc, sh, L, extra_rows=S)
-    train_study = _i32(lay.label_study)
+    train_study = lay_dev(lay, "label_study")
     if ndn:
         group_sum_fixed_into(Cq, nq, L, train_study, S)
     C, n_valid = centroids_finish(Cq, nq)
@@ -795,7 +918,7 @@ def train_model(X, lay: LabelLayout):
     rc = local_ranked_cells(*_device_matrix(X), sh, 1)
     L = len(lay.row_labels)
     C, n_valid = centroids_finish(*_label_centroids(rc, sh, L))
-    flags = _gather_cells(rc.flags, sh, to_device(sh.gidx) if world > 1 else None)
+    flags = _gather_cells(rc.flags, sh, sh.on_device("gidx", lambda: to_device(sh.gidx)) if world > 1 else None)
     return dict(centroids=C[:, :rc.G].cpu().numpy(), n_cells=n_valid.cpu().numpy(), flags=flags.cpu().numpy())
 
 

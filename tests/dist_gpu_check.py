@@ -98,6 +98,8 @@ def main():
     M._dist_info = saved
     assert np.array_equal(tab.values, ref.values, equal_nan=True), "gene-set sharded table differs"
     dist.barrier()
+    engine.release_peer_buffers()
+    dist.barrier()
     if rank == 0:
         print(f"dist check ok on {dist.get_world_size()} GPUs: full-network, centroid, pretrained, trainModel and "
               "supervised tables bit-identical")
