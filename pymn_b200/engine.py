@@ -1380,6 +1380,9 @@ def supervised_geneset(ctx: SupervisedContext, col_index: torch.Tensor, n_types:
     return auc
 
 
+SUP_STREAMS = int(_os.environ.get("MN_SUP_STREAMS", "2"))
+
+
 def supervised_tables(ctx: SupervisedContext, all_cols: torch.Tensor, offs, n_types: int, ndn=True, fast=False,
                       nbins=DEFAULT_NBINS):
     """All gene sets of one rank, back to back on the current stream (MetaNeighbor.py:84-93).  ``all_cols``:
@@ -1406,6 +1409,24 @@ def supervised_tables(ctx: SupervisedContext, all_cols: torch.Tensor, offs, n_ty
     spill = None
     if not fast and n_sets > 0:
         spill = rho_spill_buffer(N, 0, 1, nbins, dev, reserve_bytes=N * (S * K + 1) * 8 + N * K * 4 + (2 << 30))
+    n_streams = SUP_STREAMS if (not fast and n_sets >= 4 and spill is not None and spill[0] is not None) else 1
+    if n_streams > 1:
+        # Full-network mode, gene sets alternate between two streams (each with its own rho spill): the small
+        # kernels of one set (K1, CDF table, LOSO combination, AUROC: ~0.13 of its 0.75 ms, none of which fills the
+        # machine) run under the two network passes of the other.
+        cur = torch.cuda.current_stream()
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        need = int(spill[1]) * int(LAST_SPILL["tile_bytes"])         # (the cached buffer may be far larger than this run needs)
+        spills = [spill] + [(torch.empty((need,), dtype=torch.uint8, device=dev), spill[1]) for _ in range(n_streams - 1)]
+        for st_ in streams:
+            st_.wait_stream(cur)
+        for j in range(n_sets):
+            with torch.cuda.stream(streams[j % n_streams]):
+                supervised_geneset(ctx, all_cols[int(offs[j]):int(offs[j + 1])], K, ndn, fast, nbins,
+                                   out=tables[j], spill=spills[j % n_streams])
+        for st_ in streams:
+            cur.wait_stream(st_)
+        return tables, poison
     for j in range(n_sets):
         supervised_geneset(ctx, all_cols[int(offs[j]):int(offs[j + 1])], K, ndn, fast, nbins,
                            poison_out=poison[j:j + 1] if fast else None, out=tables[j], spill=spill)
