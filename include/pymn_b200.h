@@ -39,7 +39,7 @@ typedef uint16_t mn_half_t;  /* IEEE binary16 bit pattern (__half) */
 
 /* ---- library ------------------------------------------------------------- */
 const char* mn_last_error(void);
-int mn_abi_version(void);
+int mn_abi_version(void);              /* 3 = round 2 (limb / fixed-point / peer / batch entry points added) */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t mn_launch_count(void);
 

@@ -24,7 +24,7 @@ extern "C" {
 
 const char* mn_last_error(void) { return mn::g_err; }
 
-int mn_abi_version(void) { return 2; }
+int mn_abi_version(void) { return 3; }
 
 int64_t mn_launch_count(void) { return (int64_t)mn::g_launches.load(std::memory_order_relaxed); }
 

@@ -63,7 +63,7 @@ def test_shared_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert _lib.load().mn_abi_version() == 2
+    assert _lib.load().mn_abi_version() == 3
 
 
 def test_product_path_fails_loudly_without_gpu():
