@@ -22,12 +22,13 @@ from .model_io import load_model, save_model
 def release_caches():
     """Give back the device memory the package keeps between calls: the rho spill of the full-network path (up to
     ~80 GB for 200,000 cells: allocating it costs more than a call, so it is cached -- ``MN_SPILL_GB`` caps it, ``0``
-    disables the spill), the multi-GPU peer receive buffers and the pinned upload staging area.  On several GPUs call
+    disables the spill), the multi-GPU peer receive buffers, the device buffer of the streamed upload and the pinned staging area.  On several GPUs call
     it on every rank."""
     from . import engine
     engine.release_spill_cache()
     engine.release_peer_buffers()
     engine._STAGE.clear()
+    engine._XD_CACHE.clear()
 
 
 __all__ = ["MetaNeighborUS", "MetaNeighbor", "trainModel", "variableGenes", "join_labels", "AnnDataLite", "save_model", "load_model",

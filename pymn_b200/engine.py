@@ -1149,6 +1149,10 @@ STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "16"))
 STREAM_DEV_CHUNKS = int(_os.environ.get("MN_STREAM_DEV_CHUNKS", "6"))
 
 
+_XD_CACHE = {}          # device index -> uint8 buffer holding the streamed upload of the current call
+_SIDE_STREAMS = {}      # device index -> the upload stream
+
+
 def start_upload(X, full_network: bool = False):
     """Begin moving the expression matrix to the device.  A large dense float32 matrix in PINNED host memory
     is sent in row chunks, last rows first, on a side stream (AsyncUpload): the full-network pipeline
@@ -1170,12 +1174,25 @@ def start_upload(X, full_network: bool = False):
         if t.is_pinned():
             dev = _dev()
             N = int(X.shape[0])
-            Xd = torch.empty(tuple(X.shape), dtype=torch.float32, device=dev)
-            side = torch.cuda.Stream(device=dev)
+            # The device copy lives in a buffer kept between calls.  A fresh tensor per call would have to be marked
+            # as used by the side stream (record_stream), which delays the reuse of its block: every other call then
+            # pays a cudaMalloc of the whole matrix (observed: calls alternating between 122 and 162 ms).  Ordering is
+            # by streams instead: the side stream waits for everything queued on the current one (the previous
+            # call's kernels, which read the buffer) before the first chunk is copied.
+            nbytes = int(X.nbytes)
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            buf = _XD_CACHE.get(idx)
+            if buf is None or buf.numel() < nbytes:
+                _XD_CACHE.pop(idx, None)
+                buf = None
+                buf = _XD_CACHE[idx] = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            Xd = buf[:nbytes].view(torch.float32).view(tuple(X.shape))
+            side = _SIDE_STREAMS.get(idx)
+            if side is None:
+                side = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             bounds = [int(round(k * N / STREAM_CHUNKS)) for k in range(STREAM_CHUNKS + 1)]
             pending = [(bounds[k], bounds[k + 1]) for k in reversed(range(STREAM_CHUNKS)) if bounds[k + 1] > bounds[k]]
-            Xd.record_stream(side)
             up = AsyncUpload(Xd, t, side, pending)
             up.enqueue(max(1, int(round(STREAM_EARLY_BYTES / max(1, X.nbytes // STREAM_CHUNKS)))))
             return up
