@@ -555,6 +555,10 @@ def run_ours(args):
             t1 = time.perf_counter()
             torch.cuda.synchronize()
             _lib.call = orig
+            if rank == 0 and engine.UPLOAD_LOG:
+                sys.stderr.write("   upload chunks (rows, host enqueue ms, device done ms): " + " ".join(
+                    f"[{lo // 1000}k {1e3 * (th - t0):.1f} {ev0.elapsed_time(ev):.1f}]" for lo, hi, ev, th in engine.UPLOAD_LOG) + "\n")
+            engine.UPLOAD_LOG.clear()
             if rank == 0:
                 sys.stderr.write(f"traced e2e call {rep}: wall {1e3 * (t1 - t0):.1f} ms\n")
                 for name, t, ev in log:

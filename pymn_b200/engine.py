@@ -75,7 +75,12 @@ def to_device(x, dtype=None):
         if a.nbytes >= (8 << 20) and not t.is_pinned():
             t = _upload_pageable(a, dev)
         else:
-            if a.nbytes >= (1 << 20):
+            # Anything above 32 KB goes through pinned memory (torch's caching host allocator: ~0.1 ms for 1 MB).  A
+            # PAGEABLE copy of more than 64 KB is staged piecewise by the driver, and its later pieces queue in the copy
+            # engine behind whatever was issued meanwhile -- e.g. the 1.2 GB train of the streamed matrix upload: the
+            # label arrays then arrive 20 ms late and the first kernel with them (tools/h2d_probe.py: a stream
+            # waiting for the 3rd of 12 queued copies resumes at 5.5 ms without, at 21.7 ms with such a copy).
+            if a.nbytes >= (32 << 10):
                 t = t.pin_memory()
             t = t.to(dev, non_blocking=True)
     if dtype is not None and t.dtype != dtype:
@@ -1094,6 +1099,11 @@ def network_from_ranked(rc: RankedCells, cell_label, seg_off, L, S, ndn=True, nb
     return auc, n_pos, rc.flags, hist
 
 
+import time as _time
+TRACE_UPLOAD = bool(_os.environ.get("MN_TRACE_UPLOAD"))       # diagnostic: timing-enabled chunk events, logged
+UPLOAD_LOG = []
+
+
 class AsyncUpload:
     """A dense host matrix on its way to the device: row chunks copied LAST ROWS FIRST on a side stream,
     one event per chunk.  ``chunks`` = [(row_lo, row_hi, event)] in upload order."""
@@ -1113,9 +1123,11 @@ class AsyncUpload:
             for _ in range(n):
                 lo, hi = self._pending.pop(0)
                 self.Xd[lo:hi].copy_(self._host[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=TRACE_UPLOAD)
                 ev.record(self._side)
                 self.chunks.append((lo, hi, ev))
+                if TRACE_UPLOAD:
+                    UPLOAD_LOG.append((lo, hi, ev, _time.perf_counter()))
 
     def event_for_rows_from(self, row_lo: int):
         """Event after which every input row >= row_lo is on the device."""
