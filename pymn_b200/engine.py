@@ -1129,6 +1129,23 @@ class AsyncUpload:
                 if TRACE_UPLOAD:
                     UPLOAD_LOG.append((lo, hi, ev, _time.perf_counter()))
 
+    def upload_small(self, arrays):
+        """int32 device copies of small host arrays, copied on the upload stream (FIFO with the matrix chunks queued
+        so far); the current stream waits for them."""
+        cur = torch.cuda.current_stream()
+        dev = self.Xd.device
+        hosts = [torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32))).pin_memory() for a in arrays]
+        outs = [torch.empty(h.shape, dtype=torch.int32, device=dev) for h in hosts]      # allocated for the current stream
+        self._side.wait_stream(cur)              # (their blocks may have been in use by work queued on the current stream)
+        with torch.cuda.stream(self._side):
+            for o, h in zip(outs, hosts):
+                o.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        cur.wait_event(ev)
+        self._small = hosts                      # keep the pinned sources alive until the call is over
+        return outs
+
     def event_for_rows_from(self, row_lo: int):
         """Event after which every input row >= row_lo is on the device."""
         self.enqueue()
@@ -1223,7 +1240,10 @@ def us_default_streamed(up: AsyncUpload, lay: LabelLayout, L, S, ndn=True, nbins
     N, G = up.shape
     cur = torch.cuda.current_stream()
     perm_np = np.asarray(lay.perm)
-    perm, cell_label, seg_off = _i32(lay.perm), _i32(lay.cell_label), _i32(lay.seg_off)
+    # The label arrays travel on the UPLOAD stream, between the chunks queued so far and the rest of the matrix: the
+    # copy engine drains one stream's queue before it serves another's, so a copy issued on the compute stream while
+    # matrix chunks are in flight would only run after the whole 1.6 GB (the first kernel then starts 20 ms late).
+    perm, cell_label, seg_off = up.upload_small([lay.perm, lay.cell_label, lay.seg_off])
     up.enqueue()                                 # the rest of the matrix follows the small arrays through the copy engine
     nd = max(1, min(STREAM_DEV_CHUNKS if STREAM_DEV_CHUNKS > 0 else STREAM_CHUNKS, N // 4096))
     # (row chunks start on multiples of 512: the tile height of the widest GEMM form)
