@@ -468,26 +468,53 @@ one_vs_best_kernel(const float* __restrict__ votes, int64_t ldv, int ncols, cons
         const int b0 = lab_row_off[lb0 + best], b1 = lab_row_off[lb0 + best + 1];
         const int c0 = lab_row_off[lb0 + cont], c1 = lab_row_off[lb0 + cont + 1];
         unsigned long long u2 = 0, nb = 0, ncn = 0;
-        const float qnan = __int_as_float(0x7fc00000);
+        const float pinf = __int_as_float(0x7f800000);
         for (int cc = c0; cc < c1; cc += OCHUNK) {
             const int m = min(OCHUNK, c1 - cc);
             __syncthreads();
             for (int j = tid; j < m; j += OT) {
                 const bool ok = cell_label[cc + j] >= 0;
-                s_vals[j] = ok ? vote_value(v, dn, cc + j) : qnan;
+                s_vals[j] = ok ? vote_value(v, dn, cc + j) : pinf;
                 ncn += ok ? 1 : 0;
             }
+            // sort the contender's chunk (bitonic, +inf = excluded cell / padding), then every cell of the best label
+            // counts the smaller and the equal votes with two binary searches: the same integers as comparing
+            // all pairs, at ~1/6 of the instructions for ~500-cell clusters
+            int P = 32;
+            while (P < m) P <<= 1;
+            for (int j = m + tid; j < P; j += OT) s_vals[j] = __int_as_float(0x7f800000);
             __syncthreads();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (int t = tid; t < P; t += OT) {
+                        const int ixj = t ^ jj;
+                        if (ixj > t) {
+                            const float a = s_vals[t], b = s_vals[ixj];
+                            const bool up = (t & k) == 0;
+                            if ((a > b) == up) {
+                                s_vals[t] = b;
+                                s_vals[ixj] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
             for (int i = b0 + tid; i < b1; i += OT) {
                 if (cell_label[i] < 0) continue;
                 const float vi = vote_value(v, dn, i);
-                unsigned int local = 0;
-#pragma unroll 8
-                for (int j = 0; j < m; ++j) {
-                    const float vj = s_vals[j];
-                    local += (vi > vj) ? 2u : ((vi == vj) ? 1u : 0u);
+                int lo = 0, hi = P;                          // first position with s_vals[pos] >= vi
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_vals[mid] < vi) lo = mid + 1; else hi = mid;
                 }
-                u2 += local;
+                const int less = lo;
+                hi = P;                                      // first position with s_vals[pos] > vi
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_vals[mid] <= vi) lo = mid + 1; else hi = mid;
+                }
+                u2 += 2u * (unsigned)less + (unsigned)(lo - less);
             }
         }
         for (int i = b0 + tid; i < b1; i += OT) nb += (cell_label[i] >= 0) ? 1 : 0;
