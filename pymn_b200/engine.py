@@ -1162,12 +1162,94 @@ class AsyncUpload:
         return self.Xd
 
 
+class StagedUpload(AsyncUpload):
+    """The same for a PAGEABLE host matrix: a worker thread copies the rows (last rows first) through the two pinned
+    64 MB staging buffers and queues each piece on the upload stream -- the host copy of piece i + 1 runs while the
+    DMA engine drains piece i, and both run while the main thread encodes the labels and launches the kernels of the
+    chunks that have arrived.  (torch's large host copies release the GIL.)"""
+
+    def __init__(self, Xd, host, side, pending):
+        import threading
+        super().__init__(Xd, host, side, pending)
+        self._cond = threading.Condition()
+        self._err = None
+        self._done = False
+        self._dev = Xd.device
+        self._thread = threading.Thread(target=self._run, name="pymn_b200-upload", daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        try:
+            torch.cuda.set_device(self._dev)
+            idx = self._dev.index if self._dev.index is not None else torch.cuda.current_device()
+            if idx not in _STAGE:
+                _STAGE[idx] = (torch.empty((2, STAGE_BYTES), dtype=torch.uint8, pin_memory=True),
+                               [torch.cuda.Event(), torch.cuda.Event()])
+            stage, evs = _STAGE[idx]
+            row_bytes = int(self._host.shape[1]) * 4
+            rows_per = max(1, STAGE_BYTES // row_bytes)
+            src = self._host.view(torch.uint8).view(self._host.shape[0], row_bytes)
+            dst = self.Xd.view(torch.uint8).view(self.Xd.shape[0], row_bytes)
+            i = 0
+            for lo, hi in list(self._pending):
+                for r0 in range(hi, lo, -rows_per):                  # last rows first inside the chunk too
+                    r1, r0 = r0, max(lo, r0 - rows_per)
+                    b = i & 1
+                    i += 1
+                    evs[b].synchronize()                            # the DMA that last used this buffer has drained
+                    m = (r1 - r0) * row_bytes
+                    stage[b, :m].view(r1 - r0, row_bytes).copy_(src[r0:r1])
+                    with torch.cuda.stream(self._side):
+                        dst[r0:r1].copy_(stage[b, :m].view(r1 - r0, row_bytes), non_blocking=True)
+                        evs[b].record(self._side)
+                ev = torch.cuda.Event(enable_timing=TRACE_UPLOAD)
+                ev.record(self._side)
+                with self._cond:
+                    self.chunks.append((lo, hi, ev))
+                    if TRACE_UPLOAD:
+                        UPLOAD_LOG.append((lo, hi, ev, _time.perf_counter()))
+                    self._cond.notify_all()
+        except BaseException as e:                                  # noqa: BLE001 -- re-raised on the caller's thread
+            self._err = e
+        finally:
+            with self._cond:
+                self._done = True
+                self._pending = []
+                self._cond.notify_all()
+
+    def enqueue(self, n_chunks=None):
+        return                                                      # the worker queues everything
+
+    def _check(self):
+        if self._err is not None:
+            raise self._err
+
+    def event_for_rows_from(self, row_lo: int):
+        with self._cond:
+            while True:
+                self._check()
+                for lo, _hi, e in self.chunks:
+                    if lo <= row_lo:
+                        return e
+                if self._done:
+                    self._check()
+                    return self.chunks[-1][2]
+                self._cond.wait(0.05)
+
+    def wait_all(self):
+        self._thread.join()
+        self._check()
+        torch.cuda.current_stream().wait_event(self.chunks[-1][2])
+        return self.Xd
+
+
 # Measured at config 2 (1.6 GB pinned matrix, B200, ~55 GB/s H2D), median of 8 calls of the public API:
 # upload-then-compute 123.5 ms; 16 upload chunks x 4 row chunks of the passes 109.8 ms (x 8: 112.1, x 16: 114.7).
 # The first streamed version gained nothing: all chunk copies were queued up front and the copy engine, which
 # serves transfers in issue order across streams, made the small label arrays -- which the first kernel
 # needs -- wait for the whole matrix.  MN_STREAM_CHUNKS=1 turns streaming off.
 SHARD_UPLOAD = _os.environ.get("MN_SHARD_UPLOAD", "1") != "0"     # multi-GPU: each rank uploads only its slice of the cells
+STAGED_UPLOAD = _os.environ.get("MN_STAGED_UPLOAD", "1") != "0"   # pageable matrices: worker-thread staging, pipelined like pinned ones
 STREAM_MIN_BYTES = 64 << 20
 STREAM_EARLY_BYTES = 400 << 20          # queued before the host encodes labels (~8 ms of PCIe Gen5)
 STREAM_CHUNKS = int(_os.environ.get("MN_STREAM_CHUNKS", "16"))
@@ -1200,7 +1282,8 @@ def start_upload(X, full_network: bool = False):
     if (STREAM_CHUNKS > 1 and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2
             and X.flags.c_contiguous and X.nbytes >= STREAM_MIN_BYTES):
         t = torch.from_numpy(X)
-        if t.is_pinned():
+        if t.is_pinned() or STAGED_UPLOAD:
+            staged = not t.is_pinned()
             dev = _dev()
             N = int(X.shape[0])
             # The device copy lives in a buffer kept between calls.  A fresh tensor per call would have to be marked
@@ -1222,6 +1305,8 @@ def start_upload(X, full_network: bool = False):
             side.wait_stream(torch.cuda.current_stream())
             bounds = [int(round(k * N / STREAM_CHUNKS)) for k in range(STREAM_CHUNKS + 1)]
             pending = [(bounds[k], bounds[k + 1]) for k in reversed(range(STREAM_CHUNKS)) if bounds[k + 1] > bounds[k]]
+            if staged:
+                return StagedUpload(Xd, t, side, pending)
             up = AsyncUpload(Xd, t, side, pending)
             up.enqueue(max(1, int(round(STREAM_EARLY_BYTES / max(1, X.nbytes // STREAM_CHUNKS)))))
             return up

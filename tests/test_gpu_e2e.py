@@ -199,6 +199,37 @@ def test_default_path_streamed_upload_identical(shuffle, monkeypatch):
     assert got["hist_total"] == ref["hist_total"] and np.array_equal(got["flags"], ref["flags"])
 
 
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_default_path_staged_pageable_upload_identical(shuffle, monkeypatch):
+    """A PAGEABLE matrix goes through the worker-thread staging (StagedUpload: pieces of the pinned staging buffers,
+    last rows first) and the same streamed pipeline; the table is identical to upload-then-compute.  The fast path
+    (wait for the whole matrix) is checked on the same upload object type."""
+    from pymn_b200 import engine
+    from pymn_b200.utils import label_layout
+    x, s, c = make_counts(12, 3, 4200, 64, 5)
+    if shuffle:
+        order = np.random.default_rng(1).permutation(x.shape[0])
+        x, s, c = x[order], s[order], c[order]
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    lay = label_layout(s, c)
+    ref = engine.us_default(x.copy(), lay, True)
+    ref_fast = engine.us_fast(x.copy(), lay, True, True)
+    monkeypatch.setattr(engine, "STREAM_MIN_BYTES", 0)
+    monkeypatch.setattr(engine, "STREAM_CHUNKS", 5)
+    monkeypatch.setattr(engine, "STAGE_BYTES", 100 * 64 * 4)          # 100 rows per staged piece
+    engine._STAGE.clear()
+    try:
+        up = engine.start_upload(x)
+        assert isinstance(up, engine.StagedUpload)
+        got = engine.us_default(up, lay, True)
+        assert np.array_equal(got["auroc"], ref["auroc"]) and np.array_equal(got["n_pos"], ref["n_pos"])
+        assert got["hist_total"] == ref["hist_total"] and np.array_equal(got["flags"], ref["flags"])
+        got_fast = engine.us_fast(engine.start_upload(x), lay, True, True)
+        assert np.array_equal(got_fast["table"], ref_fast["table"], equal_nan=True)
+    finally:
+        engine._STAGE.clear()
+
+
 # ---- variableGenes (SURVEY 8f-2) -----------------------------------------------------------
 @pytest.mark.parametrize("name", C.list_cases("var_genes"))
 def test_golden_variable_genes(name):
