@@ -29,9 +29,7 @@ def trainModel(adata, study_col, ct_col, var_genes="highly_variable"):
 
     sub = select_genes(adata, var_genes)
     X = engine.start_upload(prepare_matrix(sub.X))       # the upload runs while the host encodes the labels
-    S = np.asarray(sub.obs[study_col].values, dtype=object)
-    C = np.asarray(sub.obs[ct_col].values, dtype=object)
-    lay = label_layout(S, C)
+    lay = label_layout(sub.obs[study_col].values, sub.obs[ct_col].values)      # (Arrow-backed columns stay as they are)
     r = engine.train_model(X, lay)
     flags = r["flags"]                                   # device row order
     kept = (flags & 2) == 0                              # cells with sum > 0 (trainModel.py:36-37)
