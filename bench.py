@@ -346,7 +346,8 @@ def bench_fast_config(ctx, name):
     s, c = _labels(S, n, K)
     lay = label_layout(s, c)
     N, L = int(Xd.shape[0]), len(lay.row_labels)
-    ms, st, launches, out = ctx.timed(lambda t: engine.us_fast_device(Xd, lay, True, ovb, t), 2, 3)
+    ms, st, launches, out = ctx.timed(lambda t: engine.us_fast_device(Xd, lay, True, ovb, t), 2, 5)
+    steps_ms = list(ctx.last_step_ms)
     table = out[0].cpu().numpy()
     Xh = torch.empty((N, G), dtype=torch.float32, pin_memory=True)
     Xh.copy_(Xd)
@@ -365,6 +366,7 @@ def bench_fast_config(ctx, name):
     del Xh, ad
     return {"workload": desc, "metric": "MetaNeighborUS effective cell-pairs/s (N^2 / step; the pairs are never formed)",
             "unit": UNIT, "n_cells": N, "n_genes": G, "n_labels": L, "value": pairs / (ms / 1e3), "ms_per_step": ms,
+            "steps_ms": steps_ms,
             "e2e": {"value": pairs / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": N * G * 4 + 12 * N,
                     "d2h_bytes_per_step": L * L * 16 + N},
             "gpu_launches": launches, "stage_ms": st, "roofline": dict(kern[dom], kernel=dom), "kernels": kern,
@@ -395,7 +397,8 @@ def bench_c5(ctx):
     st_uniq, st_codes = np.unique(st_names, return_inverse=True)
     mstudy = engine._i32(st_codes.astype(np.int32))
     ms, st, launches, out = ctx.timed(
-        lambda t: engine.us_pretrained_device(Xd, lay, cent, n_cells, mstudy, len(st_uniq), True, False, t), 2, 3)
+        lambda t: engine.us_pretrained_device(Xd, lay, cent, n_cells, mstudy, len(st_uniq), True, False, t), 2, 5)
+    steps_ms = list(ctx.last_step_ms)
     table = out[0].cpu().numpy()
     Xh = torch.empty((N, G), dtype=torch.float32, pin_memory=True)
     Xh.copy_(Xd)
@@ -418,7 +421,7 @@ def bench_c5(ctx):
     del Xh, ad
     return {"workload": desc, "metric": "MetaNeighborUS effective cell-pairs/s (N_query x sum of model n_cells / step)",
             "unit": UNIT, "n_query_cells": N, "n_genes": G, "model_columns": Lt, "value": eff_pairs / (ms / 1e3),
-            "query_cells_per_s": N / (ms / 1e3), "ms_per_step": ms, "train_model_ms": train_s * 1e3,
+            "query_cells_per_s": N / (ms / 1e3), "ms_per_step": ms, "steps_ms": steps_ms, "train_model_ms": train_s * 1e3,
             "e2e": {"value": eff_pairs / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                     "query_cells_per_s": N / e2e_s, "h2d_bytes_per_step": N * G * 4 + 12 * N + Lt * G * 4,
                     "d2h_bytes_per_step": L * Lt * 16 + N},
