@@ -550,6 +550,13 @@ def local_ranked_cells(Xd, base: int, sh: CellShard, drop_mode=0):
     return rank_normalize(Xd, row_index=rows, drop_mode=drop_mode, limbs=True)
 
 
+def _reference_votes(tot: torch.Tensor, C: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """mu[n] = (mean cell) . C[n] in double, from a fixed-point cell sum ``tot`` (int64 [ldd + 1]: sums, then the count)."""
+    ldd = int(C.stride(0))
+    mean_cell = tot[:ldd].double() * (2.0 ** -38) / tot[ldd].clamp(min=1).double()
+    return (C[:n_rows].double() * mean_cell).sum(dim=1)
+
+
 def _column_reference(Xd, base: int, sh: CellShard, C: torch.Tensor, n_rows: int) -> torch.Tensor:
     """mu[n] = mean over the first min(N, REF_BLOCK) INPUT cells of x* . C[n] (double [n_rows]): the value a
     column's votes are centred on before their one float32 rounding (any constant is a monotone map of the
@@ -572,12 +579,11 @@ def _column_reference(Xd, base: int, sh: CellShard, C: torch.Tensor, n_rows: int
         tot = torch.zeros((ldd + 1,), dtype=torch.int64, device=dev)
     if sh.world > 1:
         _all_reduce_sum(tot)
-    mean_cell = tot[:ldd].double() * (2.0 ** -38) / tot[ldd].clamp(min=1).double()
-    return (C[:n_rows].double() * mean_cell).sum(dim=1)
+    return _reference_votes(tot, C, n_rows)
 
 
 def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: LabelLayout, C, n_valid, n_train, train_study,
-                             n_train_studies, ndn: bool, ovb: bool, timer=None):
+                             n_train_studies, ndn: bool, ovb: bool, timer=None, ref_tot=None):
     """predict_and_score (MetaNeighborUS.py:310-387) for all test studies at once.
     C rows [0, n_train) = cluster centroids, rows [n_train, n_train + n_train_studies) = study centroids
     (identical on every rank); ``rc`` = this rank's ranked cells (local order of ``sh``).
@@ -605,7 +611,9 @@ def _score_against_centroids(Xd, base, rc: RankedCells, sh: CellShard, lay: Labe
     # per study).
     n_b = n_train + (n_train_studies if ndn else 0)
     if t: t.start("votes_ref")
-    mu = _column_reference(Xd, base, sh, C, n_b)
+    # (the centring reference: the mean of ALL cells when the caller has their exact fixed-point sum -- the label
+    #  centroids add up to it --, else the mean of the first REF_BLOCK input cells)
+    mu = _reference_votes(ref_tot, C, n_b) if ref_tot is not None else _column_reference(Xd, base, sh, C, n_b)
     if t: t.stop("votes_ref")
     if world > 1:
         # columns in destination order: rank d's columns d, d + world, ... as one block of n_max rows (padding
@@ -871,8 +879,10 @@ def us_fast_device(X, lay: LabelLayout, ndn=True, ovb=False, timer=None):
     if ndn:
         group_sum_fixed_into(Cq, nq, L, train_study, S)
     C, n_valid = centroids_finish(Cq, nq)
+    # the label centroids add up to the exact (integer, all-reduced) sum of all kept cells: the centring reference
+    ref_tot = torch.cat([Cq[:L].sum(dim=0), nq[:L].sum().to(torch.int64).reshape(1)])
     if t: t.stop("centroids")
-    return _score_against_centroids(Xd, base, rc, sh, lay, C, n_valid, L, train_study, S, ndn, ovb, timer)
+    return _score_against_centroids(Xd, base, rc, sh, lay, C, n_valid, L, train_study, S, ndn, ovb, timer, ref_tot=ref_tot)
 
 
 def us_fast(X, lay: LabelLayout, ndn=True, ovb=False):
