@@ -547,3 +547,25 @@ def test_corr_votes_heavy_ties_mid_rank(eng):
     v0, d0, h0, _ = eng.corr_network_votes(rc, eng._i32(label), L, nbins=nb, spill_tiles=0)
     torch.cuda.synchronize()
     assert torch.equal(v0, votes) and torch.equal(d0, degree) and torch.equal(h0, hist)
+
+
+def test_node_degree_gemm_repeatable_at_scale(eng):
+    """mn_votes_den_i8 at config-4 scale (500k cells, 3,000 genes, 7 study rows): two runs are bit-identical and
+    equal the CUDA-core kernel to the last bits of a double (a tile variant once passed every small test and
+    failed here)."""
+    from pymn_b200.synth import make_counts_torch
+    S = 7
+    Xd, _, _ = make_counts_torch(4, S, 71429, 3000, 150, torch.device("cuda", 0))
+    rc = eng.rank_normalize(Xd, limbs=True)
+    del Xd
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    C = torch.randn((S, rc.ldd), device="cuda", generator=g) * 3.0
+    C[:, 3000:] = 0
+    add = torch.rand((S,), device="cuda", generator=g) * 100
+    ref = eng.votes_den64(rc, C, add, S, cuda_cores=True)
+    a = eng.votes_den64(rc, C, add, S)
+    b = eng.votes_den64(rc, C, add, S)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b), "node-degree GEMM is not repeatable"
+    rel = ((a - ref).abs() / ref.abs().clamp(min=1e-30)).max().item()
+    assert rel < 1e-14, f"node-degree GEMM differs from the CUDA-core kernel: rel {rel:.2e}"
