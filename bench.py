@@ -244,9 +244,15 @@ class Ctx:
         """Device time of `steps` calls of fn(timer) after `warmup` untimed ones: CUDA events on the current
         stream, barrier + synchronize on both sides, max over ranks.  Returns (ms per step, stage ms, launches, last result)."""
         from pymn_b200 import _lib, engine
+        import gc
         torch = self.torch
         for _ in range(warmup):
             fn(None)
+        # as `timeit` does: no cyclic garbage collection inside the timed region (a full collection of this process's
+        # heap -- a few million label strings -- takes 100-150 ms and used to land in the first timed step)
+        gc.collect()
+        gc_was = gc.isenabled()
+        gc.disable()
         self.barrier()
         timer = engine.StageTimer()
         l0 = _lib.launch_count()
@@ -260,6 +266,8 @@ class Ctx:
             marks[-1].record()
         e1.record()
         self.barrier()
+        if gc_was:
+            gc.enable()
         launches = self.sum_over_ranks(_lib.launch_count() - l0)
         ms = self.max_over_ranks(e0.elapsed_time(e1)) / steps
         self.last_step_ms = [round(self.max_over_ranks(a.elapsed_time(b)), 3) for a, b in zip(marks[:-1], marks[1:])]
@@ -267,8 +275,12 @@ class Ctx:
 
     def wall(self, fn, warmup, steps):
         """Host wall clock of the public API call (the result is a host table, so the call has synchronised)."""
+        import gc
         for _ in range(warmup):
             fn()
+        gc.collect()
+        gc_was = gc.isenabled()
+        gc.disable()
         self.barrier()
         t0 = time.perf_counter()
         out = None
@@ -278,7 +290,10 @@ class Ctx:
             out = fn()
             self.last_wall_ms.append(round((time.perf_counter() - t1) * 1e3, 2))
         self.barrier()
-        return self.max_over_ranks((time.perf_counter() - t0) / steps), out
+        dt = time.perf_counter() - t0
+        if gc_was:
+            gc.enable()
+        return self.max_over_ranks(dt / steps), out
 
 
 def _adata(X, s, c, G):
