@@ -28,19 +28,17 @@ _POOL = None
 
 
 def _pool():
-    """A small persistent thread pool for the host-side label encoding (Arrow's hash kernels release the GIL;
-    starting threads per call costs as much as the work)."""
+    """One persistent helper thread for the host-side label encoding (Arrow's hash kernels release the GIL;
+    starting a thread per call costs as much as the work)."""
     global _POOL
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="pymn_b200-labels")
+        _POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pymn_b200-labels")
     return _POOL
 
 
-def _arrow_encode_async(vec, n_slices=4):
-    """Start the dictionary encoding of an Arrow-backed pandas string array in slices on the pool; returns the list
-    of futures (each -> (int32 codes of the slice, its distinct values)) or None when ``vec`` is not Arrow-backed
-    or holds nulls."""
+def _arrow_flat(vec):
+    """The Arrow array behind a pandas string array (one chunk), or None when ``vec`` is not Arrow-backed / holds nulls."""
     arr = getattr(vec, "_pa_array", None)
     if arr is None:
         return None
@@ -48,34 +46,21 @@ def _arrow_encode_async(vec, n_slices=4):
         import pyarrow as pa
         if arr.null_count or not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
             return None
-        flat = arr.combine_chunks() if isinstance(arr, pa.ChunkedArray) else arr
+        return arr.combine_chunks() if isinstance(arr, pa.ChunkedArray) else arr
     except Exception:
         return None
-    n = len(flat)
-    k = n_slices if n >= 50_000 else 1
-    bounds = [n * i // k for i in range(k + 1)]
-
-    def work(i):
-        enc = flat.slice(bounds[i], bounds[i + 1] - bounds[i]).dictionary_encode()
-        return np.asarray(enc.indices.to_numpy(zero_copy_only=False), dtype=np.int32), enc.dictionary.to_pylist()
-    if k == 1:
-        class _Done:
-            def __init__(self, v):
-                self._v = v
-
-            def result(self):
-                return self._v
-        return [_Done(work(0))]
-    return [_pool().submit(work, i) for i in range(k)]
 
 
-def _arrow_finish(futures):
-    """Sorted distinct values (code-point order, as np.unique) and int32 codes from the slice encodings."""
-    parts = [f.result() for f in futures]
-    names = sorted(set().union(*[p[1] for p in parts]))
+def _arrow_encode(flat):
+    """Sorted distinct values (code-point order, as np.unique) and int32 codes of an Arrow string array: Arrow's own
+    dictionary encoding (the hash kernel runs without the GIL), then a remap of the handful of distinct values."""
+    enc = flat.dictionary_encode()
+    codes = np.asarray(enc.indices.to_numpy(zero_copy_only=False), dtype=np.int32)
+    first_seen = enc.dictionary.to_pylist()
+    names = sorted(first_seen)
     pos = {v: i for i, v in enumerate(names)}
-    codes = [np.asarray([pos[v] for v in d], dtype=np.int32)[c] if len(d) else c for c, d in parts]
-    return np.array(names, dtype=object), (np.concatenate(codes) if len(codes) > 1 else codes[0])
+    remap = np.asarray([pos[v] for v in first_seen], dtype=np.int32)
+    return np.array(names, dtype=object), (remap[codes] if len(first_seen) else codes)
 
 
 def _factorize_sorted(vec):
@@ -88,9 +73,9 @@ def _factorize_sorted(vec):
         vec = vec.values
     if not isinstance(vec, np.ndarray) and getattr(getattr(vec, "dtype", None), "name", "") == "category":
         vec = np.asarray(vec, dtype=object)
-    fut = _arrow_encode_async(vec)
-    if fut is not None:
-        return _arrow_finish(fut)
+    flat = _arrow_flat(vec)
+    if flat is not None:
+        return _arrow_encode(flat)
     # hash-factorise the N cells (O(N)), then sort only the handful of distinct values
     codes, uniq = pd.factorize(vec, sort=False)
     if (codes < 0).any():                      # missing values: the reference would stringify them ("nan")
@@ -148,18 +133,17 @@ class LabelLayout:
 
 
 def _factorize_two(a, b):
-    """The two obs columns are factorised side by side: Arrow-backed string columns in slices on the persistent
-    pool (the hash kernels release the GIL), anything else through pandas' hash tables on two threads."""
+    """The two obs columns are factorised side by side: one on the persistent helper thread, one on the calling
+    thread (Arrow's hash kernels and pandas' hash tables release the GIL).  One hand-off per call, on purpose: with
+    eight slice tasks on four threads the interpreter's 5 ms GIL switch interval showed up as sporadic 50 ms calls."""
     import pandas as pd
     a = a.values if isinstance(a, pd.Series) else a
     b = b.values if isinstance(b, pd.Series) else b
-    fa, fb = _arrow_encode_async(a), _arrow_encode_async(b)
-    if fa is not None and fb is not None:
-        return _arrow_finish(fa), _arrow_finish(fb)
-    if len(a) < 100_000:
+    if len(a) < 50_000:
         return _factorize_sorted(a), _factorize_sorted(b)
-    ra, rb = _pool().submit(_factorize_sorted, a), _pool().submit(_factorize_sorted, b)
-    return ra.result(), rb.result()
+    fb = _pool().submit(_factorize_sorted, b)
+    ra = _factorize_sorted(a)
+    return ra, fb.result()
 
 
 def label_layout(study, ctype, replace_bar=False) -> LabelLayout:
