@@ -1687,10 +1687,13 @@ static int votes_i8(int low_only, PeerOut peer, const int8_t* a1, const int8_t* 
     }
     // CTA pairs (cta_group::2, 256 x 128 tiles: each CTA stages its own 128 rows of A and HALF of every B digit
     // tile) when there are enough row tiles to keep every pair busy; MN_I8_CTAS=1 / 2 forces a form
-    int ctas = (M >= (int64_t)2 * BM * sm_count()) ? 2 : 1;
+    // a handful of columns (the node-degree rows, the supervised path's joint labels): 128 x 64 tiles of single CTAs --
+    // half the MMA work of a 128-wide tile, and TMEM then holds two accumulator stages
+    const bool narrow = (Nn <= 64 && !peer.ptrs && !getenv("MN_I8_WIDE"));
+    int ctas = (!narrow && M >= (int64_t)2 * BM * sm_count()) ? 2 : 1;
     if (const char* e = getenv("MN_I8_CTAS")) {
         const int v = atoi(e);
-        if (v == 1 || v == 2) ctas = v;
+        if (!narrow && (v == 1 || v == 2)) ctas = v;
     }
     if (peer.ptrs) {
         MN_CHECK_ARG(peer.world >= 2 && peer.world <= 8 && peer.src >= 0 && peer.src < peer.world && peer.cols >= 1 &&
@@ -1720,8 +1723,8 @@ static int votes_i8(int low_only, PeerOut peer, const int8_t* a1, const int8_t* 
     p.col_den = col_den;
     p.col_scale = col_scale;
     p.ldo = ldo;
-    // (a 128 x 64-tile instantiation for the few node-degree columns -- double-buffered accumulators -- measured 2.3x
-    //  faster but produced wrong, non-repeatable sums at M = 500,000 while passing every small test: not shipped)
+    if (narrow)
+        return launch_gemm<64, EPI_STORE, 4, 1, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
     if (ctas == 2)
         return launch_gemm<128, EPI_STORE, 4, 2, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
     return launch_gemm<128, EPI_STORE, 4, 1, EPI_WARPS, 1>(a1, a0, lda, M, b_limbs, nullptr, ldb, Nn, G, p, (cudaStream_t)stream);
