@@ -25,6 +25,10 @@ def join_labels(x, y, replace_bar=False):
 
 
 _POOL = None
+# Encode the two obs columns on two threads (1) or one after the other (0, the default).  The helper thread saves
+# ~1.5 ms of a 200,000-cell call -- and, on busy hosts, costs a 30-60 ms stall every few calls when the sleeping
+# thread is woken late (measured back to back on one box: 104-106 ms with one 167 ms call, against 106-108 ms flat).
+LABEL_HELPER = __import__("os").environ.get("MN_LABEL_HELPER", "0") != "0"
 
 
 def _pool():
@@ -139,7 +143,7 @@ def _factorize_two(a, b):
     import pandas as pd
     a = a.values if isinstance(a, pd.Series) else a
     b = b.values if isinstance(b, pd.Series) else b
-    if len(a) < 50_000:
+    if len(a) < 50_000 or not LABEL_HELPER:
         return _factorize_sorted(a), _factorize_sorted(b)
     fb = _pool().submit(_factorize_sorted, b)
     ra = _factorize_sorted(a)
