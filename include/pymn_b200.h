@@ -11,7 +11,9 @@
  * Conventions
  *  - plain C types only; every pointer is a DEVICE pointer unless it says "host";
  *  - the caller owns all buffers (inputs, outputs, workspaces); nothing is
- *    allocated inside and nothing outlives a call except the enqueued work;
+ *    allocated inside and nothing outlives a call except the enqueued work
+ *    (one exception: a 4 KB pool of tile counters per device for the dynamic
+ *    tile scheduler of the GEMM kernels, allocated on first use);
  *  - every call enqueues on the given stream (cudaStream_t passed as void*)
  *    and returns without synchronising; thread-compatible (one stream per call);
  *  - return value 0 = success, non-zero = error; mn_last_error() returns the
@@ -23,7 +25,10 @@
  *    |d| < G.  d_hi = fp16(d) is exact for G <= 2048; otherwise d = d_hi + d_lo
  *    exactly with both fp16.  These feed the tcgen05 kind::f16 tensor-core GEMMs
  *    with FP32 accumulation in TMEM (integer-exact operands instead of a
- *    3xTF32 split of normalised floats).
+ *    3xTF32 split of normalised floats);
+ *  - int8 "limbs" (the centroid paths): the same integers as d = 128 a1 + a0,
+ *    a0 in [-64, 63]; they feed the tcgen05 kind::i8 GEMM with int32
+ *    accumulators, whose dot products are exact.
  */
 #ifndef PYMN_B200_H
 #define PYMN_B200_H

@@ -12,6 +12,12 @@ Pipelines (reference call stacks in SURVEY.md section 3):
   us_default       metaNeighborUS_default                    MetaNeighborUS.py:145-224, utils.py:35-75
   train_model      trainModel                                trainModel.py:29-48
   supervised_*     score_default / score_low_mem             MetaNeighbor.py:106-245
+
+Multi-GPU (one process per GPU, torch.distributed / NCCL): the centroid pipelines shard the CELLS
+(cell_shard: integer all-reduce of fixed-point centroid sums, vote GEMM storing into peer GPUs' receive buffers,
+all-gather of the table's column slices), the full-network pipeline shards the row tiles of its two passes
+(integer all-reduces), the supervised pipeline shards the gene sets.  Uploads: AsyncUpload (pinned host matrix),
+StagedUpload (pageable, worker-thread staging), ShardedUpload (each rank its slice of the cells).
 """
 from __future__ import annotations
 
