@@ -213,3 +213,47 @@ def test_gene_count_limit_is_reported_early():
         pymn_b200.MetaNeighborUS(ad, "s", "c", fast_version=True)
     with pytest.raises(ValueError, match="16384"):
         pymn_b200.trainModel(ad, "s", "c")
+
+
+def test_gc_paused_restores_collector_state():
+    """The public entry points pause the cyclic GC for the duration of a call and restore whatever state they found."""
+    import gc
+    from pymn_b200.utils import gc_paused, with_gc_paused
+    was = gc.isenabled()
+    try:
+        gc.enable()
+        with gc_paused():
+            assert not gc.isenabled()
+        assert gc.isenabled()
+        gc.disable()
+        with gc_paused():
+            assert not gc.isenabled()
+        assert not gc.isenabled()                     # it was off before: stays off
+
+        @with_gc_paused
+        def f(a, b=2):
+            """doc"""
+            assert not gc.isenabled()
+            raise ValueError("boom")
+        gc.enable()
+        with pytest.raises(ValueError):
+            f(1)
+        assert gc.isenabled() and f.__doc__ == "doc"
+    finally:
+        (gc.enable if was else gc.disable)()
+
+
+def test_label_layout_helper_thread_and_sequential_agree(monkeypatch):
+    """MN_LABEL_HELPER: encoding the second obs column on the helper thread gives the layout of the sequential default."""
+    import pymn_b200.utils as U
+    rng = np.random.default_rng(5)
+    n = 60_000
+    df = pd.DataFrame({"s": np.array([f"s{v}" for v in rng.integers(0, 4, size=n)], dtype=object),
+                       "c": np.array([f"c{v}" for v in rng.integers(0, 30, size=n)], dtype=object)})
+    outs = []
+    for helper in (False, True):
+        monkeypatch.setattr(U, "LABEL_HELPER", helper)
+        outs.append(label_layout(df["s"].values, df["c"].values))
+    for f in ("perm", "cell_label", "cell_study", "seg_off", "lab_row_off", "seg_lab_off", "label_study", "sorted_pos"):
+        assert np.array_equal(getattr(outs[0], f), getattr(outs[1], f)), f
+    assert list(outs[0].row_labels) == list(outs[1].row_labels)
